@@ -1,0 +1,433 @@
+// ref_tool.cpp -- drives the REFERENCE's own tape library (libtractor_ref.so,
+// built from /root/reference by this directory's Makefile) to produce the
+// fixtures and CPU baselines every parity claim is pinned to.
+//
+//   ref_tool registry <out.txt>
+//       dump Operator::all(): name, argument sizes/directions/lane types
+//   ref_tool optests <out.trxb> [suffix=8d|d] [seed=N]
+//       one single-instruction program per registered compute op plus its
+//       buildGradients() derivatives, random inputs, and SimpleEngine outputs
+//       (same construction as tractor/src/test/test.cpp:565-588)
+//   ref_tool record <out.trxb> problem=dexsyn|fkchain kind=... frames=T tiles=K ...
+//       record a synthetic problem through the reference Var<> API, derive
+//       prep/fprop/bprop/hprop/accu with the reference's buildGradients(), run
+//       the reference SimpleEngine on K lane tiles and store residuals,
+//       gradient, tangent and Gauss-Newton products as golden arrays
+//   ref_tool bench <in.trxb> threads=N seconds=S [engine=simple|loop]
+//       time objective+gradient (x_prog, x_prep, x_bprop) on N host threads,
+//       each with its own Memory (engine.h:44-48 are const)
+//
+// TEST INFRASTRUCTURE ONLY.
+#include <atomic>
+#include <fstream>
+#include <thread>
+
+#include "ref_backend.h"
+#include "../../robio_2021_dexopt_b200/csrc/assembly/dexsyn_assemble.h"
+
+using namespace refc;
+typedef tractor::Batch8d Lane;
+
+static std::map<std::string, std::string> parseArgs(int argc, char **argv, int first) {
+  std::map<std::string, std::string> kv;
+  for (int i = first; i < argc; i++) {
+    std::string a = argv[i];
+    auto eq = a.find('=');
+    if (eq == std::string::npos) throw std::runtime_error("expected key=value: " + a);
+    kv[a.substr(0, eq)] = a.substr(eq + 1);
+  }
+  return kv;
+}
+static std::string getS(const std::map<std::string, std::string> &kv, const std::string &k, const std::string &d) {
+  auto it = kv.find(k);
+  return it == kv.end() ? d : it->second;
+}
+static long getI(const std::map<std::string, std::string> &kv, const std::string &k, long d) {
+  auto it = kv.find(k);
+  return it == kv.end() ? d : std::atol(it->second.c_str());
+}
+static double getD(const std::map<std::string, std::string> &kv, const std::string &k, double d) {
+  auto it = kv.find(k);
+  return it == kv.end() ? d : std::atof(it->second.c_str());
+}
+
+static const char *modeName(const tractor::Operator *op) {
+  if (op->isMode<tractor::compute>()) return "compute";
+  if (op->isMode<tractor::prepare>()) return "prepare";
+  if (op->isMode<tractor::forward>()) return "forward";
+  if (op->isMode<tractor::reverse>()) return "reverse";
+  return "other";
+}
+
+// ------------------------------------------------------------------ registry
+
+static int cmdRegistry(const std::string &path) {
+  auto ops = tractor::Operator::all();
+  std::sort(ops.begin(), ops.end(),
+            [](const tractor::Operator *a, const tractor::Operator *b) { return a->name() < b->name(); });
+  std::ofstream f(path);
+  for (auto *op : ops) {
+    const std::string &n = op->name();
+    bool d = n.size() > 2 && n.substr(n.size() - 2) == "_d";
+    bool d8 = n.size() > 3 && n.substr(n.size() - 3) == "_8d";
+    if (!d && !d8) continue;
+    f << n << " " << modeName(op) << " " << op->argumentCount();
+    for (auto &arg : op->arguments()) {
+      uint8_t lanes, elem;
+      classify(arg.typeInfo(), lanes, elem);
+      f << " " << arg.size() << ":" << (arg.isInput() ? "i" : "o") << ":" << (int)lanes << ":" << (int)elem;
+    }
+    f << "\n";
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ per-op tests
+
+static bool endsWith(const std::string &s, const std::string &suffix) {
+  return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
+static int cmdOpTests(const std::string &path, const std::map<std::string, std::string> &kv) {
+  std::string suffix = "_" + getS(kv, "suffix", "8d");
+  dexsyn::Rng rng((uint64_t)getI(kv, "seed", 7));
+  auto ops = tractor::Operator::all();
+  std::sort(ops.begin(), ops.end(),
+            [](const tractor::Operator *a, const tractor::Operator *b) { return a->name() < b->name(); });
+  trxfile::Bundle bundle;
+  std::string listing;
+  for (auto *op : ops) {
+    if (!op->isMode<tractor::compute>()) continue;
+    if (!endsWith(op->name(), suffix)) continue;
+    bool ok = true;
+    for (auto &arg : op->arguments()) {
+      uint8_t lanes, elem;
+      classify(arg.typeInfo(), lanes, elem);
+      if (elem != trxfile::ELEM_F64) ok = false;  // uint64 shape handles: host-callback ops
+    }
+    if (!ok) continue;
+    if (op->name().find("constraint") != std::string::npos) continue;  // out of scope
+    if (op->name().find("random") != std::string::npos || op->name().find("dropout") != std::string::npos)
+      continue;  // in-tape RNG: not reproducible even reference-vs-reference
+
+    // single-instruction program, arguments laid out back to back (test.cpp:565-588);
+    // start at 64 so that every Batch argument is 32-byte aligned
+    GradientSet gs;
+    std::vector<tractor::Program::Instruction> insts;
+    tractor::Allocator alloc(64);
+    insts.push_back((uintptr_t)op);
+    size_t in_off = 0, out_off = 0;
+    for (auto &arg : op->arguments()) {
+      size_t addr = alloc.alloc(arg.typeInfo());
+      insts.push_back(addr);
+      if (arg.isInput()) {
+        gs.prog.addInput(tractor::Program::Input(arg.typeInfo(), addr, in_off, 0));
+        in_off += arg.size();
+      } else {
+        gs.prog.addOutput(tractor::Program::Output(arg.typeInfo(), addr, out_off, 0));
+        out_off += arg.size();
+      }
+    }
+    gs.prog.updateMemorySize(alloc.top());
+    gs.prog.setInstructions(insts);
+    bool has_grad = op->tryFindVariant<tractor::forward>() && op->tryFindVariant<tractor::reverse>();
+    std::string prefix = "op/" + op->name() + "/";
+    size_t nx = portElements(gs.prog.inputs()), ny = portElements(gs.prog.outputs());
+    std::vector<double> x(nx), y, gy(ny), gx, dx(nx), dy;
+    const std::string &n = op->name();
+    for (auto &v : x) v = rng.uniform(-1, 1);
+    if (n.rfind("log_", 0) == 0 || n.rfind("sqrt_", 0) == 0)
+      for (auto &v : x) v = std::fabs(v) + 0.1;
+    if (n.rfind("div_", 0) == 0)
+      for (size_t i = nx / 2; i < nx; i++) x[i] = (x[i] < 0 ? -1 : 1) * (std::fabs(x[i]) + 0.25);
+
+    auto engine = std::make_shared<tractor::SimpleEngine>();
+    auto memory = engine->createMemory();
+    auto x_prog = engine->compile(gs.prog);
+    x_prog->run(x, memory, y);
+    bundle.programs.emplace_back(prefix + "prog", convertProgram(gs.prog));
+    bundle.arrays.emplace_back(prefix + "x", x);
+    bundle.arrays.emplace_back(prefix + "y", y);
+    if (has_grad) {
+      tractor::buildGradients(gs.prog, gs.prep, &gs.fprop, &gs.bprop);
+      // tangent-space sizes (Pose -> Twist, Quaternion -> Vector3 for scalar double; the
+      // gradient-type map has no Batch entries, type.h:55-58, so *_8d ports keep their size)
+      gy.assign(portElements(gs.bprop.inputs()), 0.0);
+      dx.assign(portElements(gs.fprop.inputs()), 0.0);
+      for (auto &v : gy) v = rng.uniform(-1, 1);
+      for (auto &v : dx) v = rng.uniform(-1, 1);
+      auto x_prep = engine->compile(gs.prep);
+      auto x_fprop = engine->compile(gs.fprop);
+      auto x_bprop = engine->compile(gs.bprop);
+      x_prep->execute(memory);
+      x_bprop->run(gy, memory, gx);
+      // fresh memory for the tangent sweep, as test.cpp:604-616 does
+      memory = engine->createMemory();
+      x_prog->run(x, memory, y);
+      x_prep->execute(memory);
+      x_fprop->run(dx, memory, dy);
+      bundle.programs.emplace_back(prefix + "prep", convertProgram(gs.prep));
+      bundle.programs.emplace_back(prefix + "fprop", convertProgram(gs.fprop));
+      bundle.programs.emplace_back(prefix + "bprop", convertProgram(gs.bprop));
+      bundle.arrays.emplace_back(prefix + "gy", gy);
+      bundle.arrays.emplace_back(prefix + "gx", gx);
+      bundle.arrays.emplace_back(prefix + "dx", dx);
+      bundle.arrays.emplace_back(prefix + "dy", dy);
+    }
+    listing += op->name() + (has_grad ? " grad\n" : " nograd\n");
+  }
+  bundle.texts.emplace_back("ops", listing);
+  trxfile::writeBundle(bundle, path);
+  std::cerr << "wrote " << path << "\n" << listing;
+  return 0;
+}
+
+// ------------------------------------------------------------------ problems
+
+// Synthetic serial FK chain with pose-residual style goals: the smallest tape
+// that exercises mul_fg_pose / fg_pose_angle_axis_pose and their adjoints.
+static void recordFkChain(GradientSet &gs, int joints, uint64_t seed, size_t &n_x, size_t &n_param_lane) {
+  dexsyn::ModelOptions mo;
+  mo.kind = "chain";
+  mo.chain_joints = joints;
+  mo.chain_contacts = 3;
+  mo.extra_fixed = 0;
+  mo.policy_hidden = -1;
+  mo.seed = seed;
+  dexsyn::Model model = dexsyn::makeModel(mo);
+  n_x = joints;
+  n_param_lane = 3;
+  MuteCout mute;
+  gs.prog.record([&]() {
+    typedef RefBackend<Lane> B;
+    B b;
+    // joint angles: shared scalar variables broadcast to the lanes, plus a per-lane offset parameter
+    std::vector<B::S> q;
+    B::S off = b.param();
+    for (int i = 0; i < joints; i++) {
+      B::W w = b.weight(0.1 * (i % 5) - 0.2);
+      B::S qi;
+      tractor::batch(w, qi);
+      q.push_back(b.add(qi, off));
+    }
+    B::S py = b.param(), pz = b.param();
+    B::P pose = b.cp(dexsyn::Joint().origin);
+    int k = 0;
+    for (size_t j = 0; j < model.joints.size(); j++) {
+      auto &jt = model.joints[j];
+      if (jt.type != dexsyn::JOINT_REVOLUTE) continue;
+      pose = b.prevolute(b.pmul(pose, b.cp(jt.origin)), q[k], b.cv(jt.axis[0], jt.axis[1], jt.axis[2]));
+      if (k % 8 == 7 || k == joints - 1) {
+        B::V3 target = b.pack(b.cs(0.2), py, pz);
+        b.goalV(b.vsub(b.pmulv(pose, b.cv(0.01, 0.02, 0.03)), target));
+        b.goalV(b.qresidual(b.porientation(pose)));
+      }
+      k++;
+    }
+  });
+  gs.build();
+}
+
+static dexsyn::Model g_model;
+
+static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::string> &kv, std::vector<double> &x0,
+                         size_t &n_param_lane) {
+  dexsyn::ModelOptions mo;
+  mo.kind = getS(kv, "kind", "handarm");
+  mo.chain_joints = (int)getI(kv, "joints", 30);
+  mo.chain_contacts = (int)getI(kv, "contacts", 16);
+  mo.extra_fixed = (int)getI(kv, "extra_fixed", 12);
+  mo.policy_hidden = (int)getI(kv, "hidden", 64);
+  mo.dropout = getI(kv, "dropout", 0) != 0;
+  mo.seed = (uint64_t)getI(kv, "seed", 20211227);
+  int frames = (int)getI(kv, "frames", 4);
+  int outer = (int)getI(kv, "outer", 1);
+  double wstd = getD(kv, "wstd", 0.1);
+  g_model = dexsyn::makeModel(mo);
+  size_t np = dexsyn::Assembler<RefBackend<Lane>>::parameterCount(g_model);
+  dexsyn::Rng rng(mo.seed + 1);
+  x0.resize(np);
+  for (auto &v : x0) v = wstd * rng.normal();
+  MuteCout mute;
+  size_t nparam = 0;
+  gs.prog.record([&]() {
+    RefBackend<Lane> b;
+    dexsyn::Assembler<RefBackend<Lane>> as(b, g_model);
+    // the reference's "outer batch" records the rollout again onto the same tape
+    // with the same weights (dexlearn.h:440-453)
+    for (int o = 0; o < outer; o++) as.rollout(frames, x0);
+    nparam = b.params.size();
+  });
+  n_param_lane = nparam;
+  gs.build();
+}
+
+// Runs K lane tiles through the reference engine and stores the golden arrays.
+static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std::vector<double> &x, size_t n_param_lane,
+                       int tiles, uint64_t seed, const std::string &param_kind) {
+  dexsyn::Rng rng(seed);
+  RefRunner run(gs);
+  size_t nx = portElements(gs.prog.inputs());
+  size_t nr = portElements(gs.prog.outputs());
+  if (x.size() != nx) throw std::runtime_error("x size mismatch");
+  std::vector<double> dx(nx);
+  for (auto &v : dx) v = rng.uniform(-1, 1);
+  bundle.arrays.emplace_back("x", x);
+  bundle.arrays.emplace_back("dx", dx);
+  std::vector<uint8_t> scalar_out;  // per output element: scalar-typed port?
+  for (auto &p : gs.prog.outputs()) {
+    uint8_t lanes, elem;
+    classify(p.typeInfo(), lanes, elem);
+    for (size_t i = 0; i < p.size() / sizeof(double); i++) scalar_out.push_back(lanes == 1);
+  }
+  std::vector<double> g_total, h_total;
+  double loss_total = 0;
+  for (int t = 0; t < tiles; t++) {
+    std::vector<double> params(n_param_lane * 8);
+    for (size_t i = 0; i < params.size(); i++) {
+      size_t port = i / 8;
+      if (param_kind == "dexsyn") {
+        // object start offsets U(-0.01,0.01), yaw U(0,2pi) (dexenv_grasp.h:151-164); dropout masks
+        if (port == 0 || port == 1) params[i] = rng.uniform(-0.01, 0.01);
+        else if (port == 2) params[i] = rng.uniform(0, 2 * M_PI);
+        else params[i] = (rng.uniform() < 0.3) ? 0.0 : 1.0 / 0.7;
+      } else {
+        params[i] = rng.uniform(-0.1, 0.1);
+      }
+    }
+    std::vector<double> r, v, g, dr, h;
+    run.parameterize(params);
+    run.forward(x, r);
+    run.prepare();
+    v = r;
+    if (t > 0)
+      for (size_t i = 0; i < v.size(); i++)
+        if (scalar_out[i]) v[i] = 0;  // lane-independent residual rows count once
+    run.reverse(v, g);
+    run.tangent(dx, dr);
+    run.gaussNewton(dx, h);
+    for (size_t i = 0; i < r.size(); i++)
+      if (!(t > 0 && scalar_out[i])) loss_total += r[i] * r[i];
+    if (t == 0) {
+      g_total = g;
+      h_total = h;
+    } else {
+      for (size_t i = 0; i < g.size(); i++) g_total[i] += g[i];
+      // hprop of a later tile re-propagates the scalar residual rows as well; remove them by
+      // running bprop on the masked tangent instead
+      std::vector<double> drm = dr, hm;
+      for (size_t i = 0; i < drm.size(); i++)
+        if (scalar_out[i]) drm[i] = 0;
+      run.reverse(drm, hm);
+      for (size_t i = 0; i < hm.size(); i++) h_total[i] += hm[i];
+    }
+    std::string s = "tile" + std::to_string(t) + "/";
+    bundle.arrays.emplace_back(s + "params", params);
+    bundle.arrays.emplace_back(s + "r", r);
+    bundle.arrays.emplace_back(s + "g", g);
+    bundle.arrays.emplace_back(s + "dr", dr);
+  }
+  bundle.arrays.emplace_back("g_total", g_total);
+  bundle.arrays.emplace_back("h_total", h_total);
+  bundle.arrays.emplace_back("loss_total", std::vector<double>{loss_total});
+  (void)nr;
+}
+
+static int cmdRecord(const std::string &path, const std::map<std::string, std::string> &kv) {
+  std::string problem = getS(kv, "problem", "dexsyn");
+  int tiles = (int)getI(kv, "tiles", 2);
+  GradientSet gs;
+  std::vector<double> x;
+  size_t n_param_lane = 0;
+  if (problem == "fkchain") {
+    size_t nx;
+    recordFkChain(gs, (int)getI(kv, "joints", 24), (uint64_t)getI(kv, "seed", 20211227), nx, n_param_lane);
+    x.resize(nx);
+    for (size_t i = 0; i < nx; i++) x[i] = 0.1 * (double)(i % 5) - 0.2 + 0.01 * (double)i;
+  } else if (problem == "dexsyn") {
+    recordDexSyn(gs, kv, x, n_param_lane);
+  } else {
+    throw std::runtime_error("unknown problem " + problem);
+  }
+  trxfile::Bundle bundle;
+  std::string meta;
+  for (auto &p : kv) meta += p.first + "=" + p.second + "\n";
+  meta += "n_x=" + std::to_string(x.size()) + "\n";
+  meta += "n_param_ports=" + std::to_string(n_param_lane) + "\n";
+  meta += "n_outputs=" + std::to_string(gs.prog.outputs().size()) + "\n";
+  {
+    size_t n = 0;
+    for (auto &i : gs.prog.instructions()) (void)i, n++;
+    meta += "n_prog_instructions=" + std::to_string(n) + "\n";
+  }
+  bundle.texts.emplace_back("meta", meta);
+  gs.addTo(bundle);
+  if (tiles > 0) goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem);
+  else bundle.arrays.emplace_back("x", x);
+  trxfile::writeBundle(bundle, path);
+  std::cerr << meta;
+  return 0;
+}
+
+// ------------------------------------------------------------------ CPU baseline
+
+static int cmdBench(const std::map<std::string, std::string> &kv) {
+  GradientSet gs;
+  std::vector<double> x;
+  size_t n_param_lane = 0;
+  recordDexSyn(gs, kv, x, n_param_lane);
+  int frames = (int)getI(kv, "frames", 4);
+  int threads = (int)getI(kv, "threads", 1);
+  double seconds = getD(kv, "seconds", 3.0);
+  bool loop = getS(kv, "engine", "simple") == "loop";
+  std::atomic<long> evals(0);
+  std::atomic<bool> stop(false);
+  std::vector<std::thread> pool;
+  std::vector<double> checks(threads, 0.0);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int ti = 0; ti < threads; ti++) {
+    pool.emplace_back([&, ti]() {
+      RefRunner run(gs, loop);  // own Memory + executables per thread
+      dexsyn::Rng rng(1000 + ti);
+      std::vector<double> params(n_param_lane * 8), r, g;
+      while (!stop.load()) {
+        for (size_t i = 0; i < params.size(); i++) {
+          size_t port = i / 8;
+          params[i] = port < 2 ? rng.uniform(-0.01, 0.01) : (port == 2 ? rng.uniform(0, 6.28) : 1.0);
+        }
+        run.parameterize(params);
+        run.forward(x, r);   // x_prog: input, execute, output
+        run.prepare();       // x_prep
+        run.reverse(r, g);   // x_bprop: input, execute, output   (gd.h:50-63)
+        checks[ti] += g[0];
+        evals.fetch_add(1);
+      }
+    });
+  }
+  while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds)
+    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  stop.store(true);
+  for (auto &t : pool) t.join();
+  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  long n = evals.load();
+  double rate = (double)n * 8.0 * frames * getI(kv, "outer", 1) / dt;  // timestep*rollouts / s
+  std::printf("{\"evals\": %ld, \"seconds\": %.4f, \"threads\": %d, \"frames\": %d, \"lanes\": 8, "
+              "\"step_rollouts_per_s\": %.3f, \"engine\": \"%s\"}\n",
+              n, dt, threads, frames, rate, loop ? "loop" : "simple");
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  try {
+    if (argc < 2) throw std::runtime_error("usage: ref_tool registry|optests|record|bench ...");
+    std::string cmd = argv[1];
+    if (cmd == "registry") return cmdRegistry(argv[2]);
+    if (cmd == "optests") return cmdOpTests(argv[2], parseArgs(argc, argv, 3));
+    if (cmd == "record") return cmdRecord(argv[2], parseArgs(argc, argv, 3));
+    if (cmd == "bench") return cmdBench(parseArgs(argc, argv, 2));
+    throw std::runtime_error("unknown command " + cmd);
+  } catch (const std::exception &e) {
+    std::cerr << "ref_tool: " << e.what() << std::endl;
+    return 1;
+  }
+}

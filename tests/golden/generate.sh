@@ -1,0 +1,19 @@
+#!/bin/bash
+# Regenerates the golden fixtures in this directory from the REFERENCE's own code.
+# Needs /root/reference (this container only); run `make -C oracle/ref_build` first.
+# Every array in these files was computed by the reference SimpleEngine
+# (tractor/src/engines/simple.cpp:22-35) on programs recorded through the reference
+# Var<> API and differentiated by the reference buildGradients() (gradients.cpp:22-407).
+set -euo pipefail
+cd "$(dirname "$0")/../.."
+R=oracle/_ref/ref_tool
+G=tests/golden
+$R registry $G/ref_registry.txt
+$R optests $G/optests_8d.trxb suffix=8d seed=7
+$R optests $G/optests_d.trxb suffix=d seed=7
+$R record $G/fkchain24.trxb problem=fkchain joints=24 tiles=2
+$R record /tmp/dexsyn_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4
+$R record /tmp/dexsyn_dropout_outer2.trxb problem=dexsyn frames=2 hidden=4 tiles=2 extra_fixed=2 dropout=1 outer=2
+xz -9 -f -c /tmp/dexsyn_small.trxb > $G/dexsyn_small.trxb.xz
+xz -9 -f -c /tmp/dexsyn_dropout_outer2.trxb > $G/dexsyn_dropout_outer2.trxb.xz
+ls -la $G
