@@ -1,0 +1,173 @@
+/* trx_b200.h -- C ABI of the B200 tape execution engine.
+ *
+ * Drop-in boundary: everything a tractor::Engine implementation needs in order
+ * to execute tractor::Program objects on a B200 (sm_100a) instead of the CPU
+ * interpreter.  Each entry point names the reference interface it stands behind
+ * (paths relative to the reference repository):
+ *
+ *   reference (C++)                                         this ABI
+ *   ------------------------------------------------------  --------------------------
+ *   Engine::createMemory()            core/engine.h:109      trx_memory_create
+ *   Engine::createExecutable()+compile core/engine.h:110-111,
+ *     Executable::_compile            core/engine.h:25,
+ *     SimpleEngine::_compile          src/engines/simple.cpp:7-20   trx_program_create[_from_blob]
+ *   Executable::_execute              core/engine.h:26,
+ *     SimpleEngine::_execute          src/engines/simple.cpp:22-35  trx_execute
+ *   Executable::_input                core/engine.h:27-28,
+ *     ExecutableBase::_input          src/engines/base.cpp:20-31    trx_input
+ *   Executable::_parameterize         core/engine.h:31-32,
+ *     ExecutableBase::_parameterize   src/engines/base.cpp:9-18     trx_parameterize
+ *   Executable::_output               core/engine.h:29-30,
+ *     ExecutableBase::_output         src/engines/base.cpp:33-40    trx_output
+ *   Executable::inputBufferSize/outputBufferSize  core/engine.h:61-68  trx_program_buffer_bytes
+ *
+ * The reference executes a tape whose scalar type is Batch<double,8>: eight
+ * rollouts ride in the lanes of every slot (dexopt/src/dexopt.cpp:16-25).  This
+ * engine generalises "8 lanes" to "R lanes" (R a multiple of the tape's lane
+ * width): a trx_memory holds R/8 lane tiles, each tile being exactly one
+ * reference memory image, and one launch executes the tape on all tiles.
+ *
+ * Packed port buffers ("wide" layout).  The reference packs ports in
+ * declaration order, each port component-major / lane-minor
+ * (src/core/recorder.cpp:514-572, geometry/vector3.h:12-13, core/batch.h:22-29).
+ * The wide layout keeps that order with 8 -> R:
+ *     scalar-typed port (double):        size bytes, once
+ *     lane-typed port (Batch<double,8>): [component][R lanes] doubles
+ * For R == 8 the wide layout is byte-identical to the reference's Buffer.
+ * Scalar-typed ports are shared by all tiles: inputs of compute/forward
+ * programs are broadcast, outputs are read from tile 0; for reverse-mode
+ * programs (bprop) scalar-typed input gradients are applied once and
+ * scalar-typed output gradients are summed over the tiles -- the reduction the
+ * reference performs lane-wise in reverse_batch (dexopt/src/ops.h:22-34).
+ *
+ * There is no CPU execution path behind this ABI: without a CUDA device every
+ * call that touches device state fails with TRX_ERR_CUDA.
+ * All functions return TRX_OK (0) or a negative status; trx_last_error() gives
+ * the message (thread local), mirroring the reference's std::runtime_error
+ * texts (core/engine.h:20-24, src/core/engine.cpp:44-48).
+ */
+#ifndef TRX_B200_H
+#define TRX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int trx_status;
+enum {
+  TRX_OK = 0,
+  TRX_ERR_INVALID = -1,     /* bad argument / malformed program                  */
+  TRX_ERR_UNSUPPORTED = -2, /* operator not implemented on the device (no fallback) */
+  TRX_ERR_CUDA = -3,        /* CUDA runtime failure or no device                 */
+  TRX_ERR_SIZE = -4         /* buffer size mismatch                              */
+};
+
+typedef struct trx_program trx_program;
+typedef struct trx_memory trx_memory;
+
+/* One operator argument, as Operator::Argument reports it (core/operator.h:84-103). */
+typedef struct trx_arg_desc {
+  uint32_t size;    /* bytes in the reference memory image */
+  uint8_t is_input; /* isInput() */
+  uint8_t lanes;    /* 1 = scalar-typed, 8 = Batch<double,8>-typed */
+  uint8_t elem;     /* 0 = f64, 1 = u64 */
+  uint8_t _pad;
+} trx_arg_desc;
+
+typedef struct trx_op_desc {
+  const char *name; /* Operator::name(), e.g. "prepare_mul_fg_pose_8d" */
+  uint32_t n_args;
+  const trx_arg_desc *args;
+} trx_op_desc;
+
+/* Program::Input / Output / Parameter / Constant (core/program.h:84-179). */
+typedef struct trx_port_desc {
+  uint64_t address; /* byte address in the memory image */
+  uint64_t offset;  /* byte offset in the reference's packed buffer / const blob */
+  uint32_t size;
+  uint8_t lanes;
+  uint8_t elem;
+  uint16_t _pad;
+} trx_port_desc;
+
+enum { TRX_SCALAR_AUTO = 0, TRX_SCALAR_SHARED = 1, TRX_SCALAR_REDUCE = 2 };
+
+/* A tractor::Program in neutral form (core/program.h:193-203). */
+typedef struct trx_program_desc {
+  uint64_t memory_size; /* Program::memorySize() */
+  uint32_t n_ops;
+  const trx_op_desc *ops; /* operator table */
+  uint64_t n_instructions;
+  uint64_t n_code_words;
+  const uint64_t *code; /* per instruction: op index, then one byte address per argument */
+  uint32_t n_inputs, n_parameters, n_outputs, n_constants;
+  const trx_port_desc *inputs, *parameters, *outputs, *constants;
+  uint64_t n_const_data;
+  const uint8_t *const_data;
+  /* How scalar-typed ports behave across lane tiles (see header comment).
+   * TRX_SCALAR_AUTO derives it from the operator modes on the tape. */
+  int32_t scalar_inputs;  /* AUTO | SHARED (broadcast) | REDUCE (apply once)   */
+  int32_t scalar_outputs; /* AUTO | SHARED (tile 0)    | REDUCE (sum of tiles) */
+} trx_program_desc;
+
+/* ---- library ------------------------------------------------------------ */
+const char *trx_last_error(void);
+const char *trx_version(void);
+/* number of CUDA devices visible; 0 means nothing below can run */
+int trx_device_count(void);
+/* operator vocabulary: number of device operators and their tape names */
+int trx_op_count(void);
+const char *trx_op_name(int index);          /* "[mode_]base" without type suffix */
+const char *trx_op_signature(int index);     /* e.g. "iT7 iT7 oT7" */
+
+/* ---- programs (Executable) ----------------------------------------------- */
+trx_status trx_program_create(const trx_program_desc *desc, int device, trx_program **out);
+/* `blob` = one program payload of a TRXB bundle (include/trx_file.h, encodeProgram) */
+trx_status trx_program_create_from_blob(const void *blob, size_t bytes, int device, trx_program **out);
+void trx_program_destroy(trx_program *p);
+
+enum {
+  TRX_BUF_INPUT = 0,
+  TRX_BUF_PARAMETER = 1,
+  TRX_BUF_OUTPUT = 2
+};
+/* bytes of the wide packed buffer of `which` ports for `lanes` rollouts */
+trx_status trx_program_buffer_bytes(const trx_program *p, int which, uint64_t lanes, uint64_t *bytes);
+/* statistics of the lowered program: n_instructions, n_levels, n_bundles, stream_words, ... */
+trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *value);
+
+/* ---- memory (Memory) ------------------------------------------------------ */
+trx_status trx_memory_create(uint64_t lanes, int device, trx_memory **out);
+void trx_memory_destroy(trx_memory *m);
+trx_status trx_memory_lanes(const trx_memory *m, uint64_t *lanes);
+/* device bytes currently held (grows on demand like MemoryImpl::resize, engines/base.h:24) */
+trx_status trx_memory_bytes(const trx_memory *m, uint64_t *bytes);
+
+/* ---- execution ------------------------------------------------------------ */
+/* `stream` is a cudaStream_t (0 = default stream).  Host-pointer variants copy
+ * through the memory's pinned staging buffer and are synchronous on return for
+ * outputs; *_device variants take device pointers in the wide layout and are
+ * fully asynchronous on `stream`. */
+trx_status trx_input(const trx_program *p, trx_memory *m, const void *packed, uint64_t bytes, void *stream);
+trx_status trx_parameterize(const trx_program *p, trx_memory *m, const void *packed, uint64_t bytes, void *stream);
+trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream);
+trx_status trx_output(const trx_program *p, trx_memory *m, void *packed, uint64_t bytes, void *stream);
+
+trx_status trx_input_device(const trx_program *p, trx_memory *m, const void *d_packed, uint64_t bytes, void *stream);
+trx_status trx_parameterize_device(const trx_program *p, trx_memory *m, const void *d_packed, uint64_t bytes,
+                                   void *stream);
+trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed, uint64_t bytes, void *stream);
+
+/* number of kernels this library has launched since load (for launch accounting) */
+uint64_t trx_kernel_launch_count(void);
+
+/* debug: copy `bytes` of tile `tile`'s memory image starting at byte `address` to the host */
+trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRX_B200_H */

@@ -1,0 +1,538 @@
+// trx_engine.cu -- the B200 tape execution engine behind include/trx_b200.h.
+//
+// One CTA executes one lane tile (8 rollouts = one reference memory image,
+// tractor/include/tractor/engines/base.h:13-31) of the tape; the W warps of the
+// CTA walk W pre-scheduled instruction streams (trx_lower.h) and meet at a
+// block barrier after every dependency level.  Tiles never interact: rollouts
+// are independent in the reference too (the only cross-lane operator is the
+// reverse of `batch`, dexopt/src/ops.h:22-34, which stays inside a tile here;
+// the sum over tiles happens when a reverse program's scalar outputs are read).
+//
+// Compiled for sm_100a only.  No CPU path: every entry point that needs the
+// device reports TRX_ERR_CUDA when there is none.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/trx_b200.h"
+#include "trx_lower.h"
+#include "vm_exec.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+trx_status fail(trx_status code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define TRX_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(TRX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+  } while (0)
+
+// ------------------------------------------------------------------ kernels
+
+// The interpreter.  grid = tiles, block = W warps.
+template <int kMaxWarps>
+__global__ void __launch_bounds__(kMaxWarps * 32)
+    trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
+                  uint64_t tile_stride) {
+  double *m = mem + (uint64_t)blockIdx.x * tile_stride;
+  const int warp = threadIdx.x >> 5;
+  const int lane32 = threadIdx.x & 31;
+  const uint32_t *pc = stream + stream_begin[warp];
+  uint32_t hdr = __ldg(pc);
+  while (true) {
+    const uint32_t op = hdr & 0x7ffu;
+    if (op == trx::OP_END) break;
+    if (op == trx::OP_BARRIER) {
+      pc += 1;
+      hdr = __ldg(pc);
+      __syncthreads();
+      continue;
+    }
+    const bool wide = (hdr >> 11) & 1u;
+    const int nsub = (int)((hdr >> 12) & 31u) + 1;
+    const int nargs = (int)((hdr >> 17) & 15u);
+    trxvm::Ctx c;
+    c.m = m;
+    int sub;
+    if (wide) {
+      sub = lane32;
+      c.as = 32;
+      c.cs = 1;
+      c.lo = 0;
+    } else {
+      sub = lane32 >> 3;
+      c.as = 4;
+      c.cs = 8;
+      c.lo = lane32 & 7;
+    }
+    c.a = pc + 1 + sub;
+    const uint32_t *next = pc + 1 + nargs * c.as;
+    hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
+    if (sub < nsub) trxvm::exec(op, c);
+    pc = next;
+  }
+}
+
+// Constants of a program into every tile (simple.cpp:27-30).
+__global__ void trx_const_kernel(const uint32_t *__restrict__ idx, const uint64_t *__restrict__ bits, uint32_t n,
+                                 double *mem, uint64_t tile_stride) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t *m = reinterpret_cast<uint64_t *>(mem + (uint64_t)blockIdx.y * tile_stride);
+  m[idx[i]] = bits[i];
+}
+
+struct DevElem {
+  uint32_t idx;
+  uint32_t fixed;
+  uint32_t per_lane;
+  uint32_t lane;  // 0xff = scalar-typed
+};
+
+// wide packed buffer -> tile images (base.cpp:9-31).  scalar_once: scalar-typed values go to tile 0
+// only and the other tiles get zero (reverse-mode programs).
+__global__ void trx_scatter_kernel(const DevElem *__restrict__ elems, uint32_t n, const double *__restrict__ wide,
+                                   uint64_t lanes, double *mem, uint64_t tile_stride, int scalar_once) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t tile = blockIdx.y;
+  DevElem e = elems[i];
+  double v;
+  if (e.lane == 0xff) {
+    v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes];
+    if (scalar_once && tile != 0) v = 0.0;
+  } else {
+    v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + tile * 8 + e.lane];
+  }
+  mem[tile * tile_stride + e.idx] = v;
+}
+
+// tile images -> wide packed buffer (base.cpp:33-40).  scalar_sum: scalar-typed values are summed
+// over the tiles in tile order (deterministic); otherwise they are read from tile 0.
+__global__ void trx_gather_kernel(const DevElem *__restrict__ elems, uint32_t n, double *__restrict__ wide,
+                                  uint64_t lanes, const double *mem, uint64_t tile_stride, uint32_t n_tiles,
+                                  int scalar_sum) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t tile = blockIdx.y;
+  DevElem e = elems[i];
+  if (e.lane == 0xff) {
+    if (tile != 0) return;
+    double v = mem[e.idx];
+    if (scalar_sum)
+      for (uint32_t t = 1; t < n_tiles; t++) v += mem[(uint64_t)t * tile_stride + e.idx];
+    wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes] = v;
+  } else {
+    wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + tile * 8 + e.lane] = mem[tile * tile_stride + e.idx];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ objects
+
+struct trx_program {
+  int device = 0;
+  trx::LoweredProgram low;
+  uint32_t *d_stream = nullptr;
+  uint64_t *d_stream_begin = nullptr;
+  uint32_t *d_const_idx = nullptr;
+  uint64_t *d_const_bits = nullptr;
+  DevElem *d_elems[3] = {nullptr, nullptr, nullptr};
+  uint32_t n_elems[3] = {0, 0, 0};
+  int scalar_inputs = TRX_SCALAR_SHARED, scalar_outputs = TRX_SCALAR_SHARED;
+  const trx::PortLayout &layout(int which) const {
+    return which == TRX_BUF_INPUT ? low.inputs : which == TRX_BUF_PARAMETER ? low.parameters : low.outputs;
+  }
+};
+
+struct trx_memory {
+  int device = 0;
+  uint64_t lanes = 0, n_tiles = 0;
+  uint64_t tile_stride = 0;  // doubles
+  double *d_mem = nullptr;
+  double *d_stage = nullptr;
+  uint64_t stage_elems = 0;
+  double *h_stage = nullptr;  // pinned
+  uint64_t h_stage_elems = 0;
+};
+
+namespace {
+
+trx_status ensureTileStride(trx_memory *m, uint64_t bytes_per_tile, cudaStream_t stream) {
+  uint64_t need = (bytes_per_tile + 255) / 256 * 256 / 8;
+  if (need <= m->tile_stride) return TRX_OK;
+  double *fresh = nullptr;
+  TRX_CUDA(cudaMalloc(&fresh, need * m->n_tiles * sizeof(double)));
+  TRX_CUDA(cudaMemsetAsync(fresh, 0, need * m->n_tiles * sizeof(double), stream));
+  if (m->d_mem) {
+    // keep what earlier programs left in the image (MemoryImpl::resize keeps contents, base.h:24)
+    TRX_CUDA(cudaMemcpy2DAsync(fresh, need * sizeof(double), m->d_mem, m->tile_stride * sizeof(double),
+                               m->tile_stride * sizeof(double), m->n_tiles, cudaMemcpyDeviceToDevice, stream));
+    TRX_CUDA(cudaStreamSynchronize(stream));
+    TRX_CUDA(cudaFree(m->d_mem));
+  }
+  m->d_mem = fresh;
+  m->tile_stride = need;
+  return TRX_OK;
+}
+
+trx_status ensureStage(trx_memory *m, uint64_t elems, bool host) {
+  if (elems > m->stage_elems) {
+    if (m->d_stage) TRX_CUDA(cudaFree(m->d_stage));
+    m->d_stage = nullptr;
+    TRX_CUDA(cudaMalloc(&m->d_stage, elems * sizeof(double)));
+    m->stage_elems = elems;
+  }
+  if (host && elems > m->h_stage_elems) {
+    if (m->h_stage) TRX_CUDA(cudaFreeHost(m->h_stage));
+    m->h_stage = nullptr;
+    TRX_CUDA(cudaMallocHost(&m->h_stage, elems * sizeof(double)));
+    m->h_stage_elems = elems;
+  }
+  return TRX_OK;
+}
+
+template <class T> trx_status upload(const std::vector<T> &v, T **dst) {
+  *dst = nullptr;
+  if (v.empty()) return TRX_OK;
+  TRX_CUDA(cudaMalloc(dst, v.size() * sizeof(T)));
+  TRX_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return TRX_OK;
+}
+
+trx_status scatterDevice(const trx_program *p, trx_memory *m, int which, const double *d_wide, uint64_t bytes,
+                         cudaStream_t stream) {
+  const trx::PortLayout &L = p->layout(which);
+  uint64_t expect = L.wideElems(m->lanes) * 8;
+  if (bytes != expect)
+    return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+                                  std::to_string(expect));
+  trx_status s = ensureTileStride(m, p->low.memory_size, stream);
+  if (s != TRX_OK) return s;
+  uint32_t n = p->n_elems[which];
+  if (n == 0) return TRX_OK;
+  dim3 grid((n + 255) / 256, (unsigned)m->n_tiles);
+  int once = (which == TRX_BUF_INPUT && p->scalar_inputs == TRX_SCALAR_REDUCE) ? 1 : 0;
+  trx_scatter_kernel<<<grid, 256, 0, stream>>>(p->d_elems[which], n, d_wide, m->lanes, m->d_mem, m->tile_stride, once);
+  g_launches++;
+  TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+trx_status scatterHost(const trx_program *p, trx_memory *m, int which, const void *packed, uint64_t bytes,
+                       cudaStream_t stream) {
+  const trx::PortLayout &L = p->layout(which);
+  uint64_t elems = L.wideElems(m->lanes);
+  if (bytes != elems * 8)
+    return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+                                  std::to_string(elems * 8));
+  if (elems == 0) return TRX_OK;
+  // the staging buffers are reused: earlier work on this stream must be done with them
+  TRX_CUDA(cudaStreamSynchronize(stream));
+  trx_status s = ensureStage(m, elems, true);
+  if (s != TRX_OK) return s;
+  std::memcpy(m->h_stage, packed, bytes);
+  TRX_CUDA(cudaMemcpyAsync(m->d_stage, m->h_stage, bytes, cudaMemcpyHostToDevice, stream));
+  return scatterDevice(p, m, which, m->d_stage, bytes, stream);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+const char *trx_last_error(void) { return g_last_error.c_str(); }
+const char *trx_version(void) { return "trx-b200 0.1 (sm_100a)"; }
+
+int trx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int trx_op_count(void) { return (int)trx::opTable().size(); }
+const char *trx_op_name(int i) {
+  auto &t = trx::opTable();
+  return (i >= 0 && i < (int)t.size()) ? t[i].tape_name.c_str() : nullptr;
+}
+const char *trx_op_signature(int i) {
+  auto &t = trx::opTable();
+  return (i >= 0 && i < (int)t.size()) ? t[i].sig : nullptr;
+}
+
+uint64_t trx_kernel_launch_count(void) { return g_launches.load(); }
+
+static trx_status createFromFile(const trxfile::Program &src, int device, int scalar_in, int scalar_out,
+                                 trx_program **out) {
+  if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  std::unique_ptr<trx_program> p(new trx_program());
+  p->device = device;
+  try {
+    trx::LowerOptions opt;
+    if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
+    trx::lowerProgram(src, opt, p->low);
+  } catch (const std::exception &e) {
+    std::string msg = e.what();
+    bool unsupported = msg.find("unsupported operator") != std::string::npos;
+    return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, msg);
+  }
+  // scalar-typed port behaviour across tiles (see trx_b200.h)
+  bool reverse_only = p->low.has_reverse && !p->low.has_forward;
+  p->scalar_inputs = scalar_in != TRX_SCALAR_AUTO ? scalar_in : (reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED);
+  p->scalar_outputs = scalar_out != TRX_SCALAR_AUTO ? scalar_out : (p->low.has_reverse ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TRX_ERR_CUDA, "no CUDA device: the tape engine has no CPU execution path");
+  TRX_CUDA(cudaSetDevice(device));
+  trx_status s;
+  if ((s = upload(p->low.stream, &p->d_stream)) != TRX_OK) return s;
+  if ((s = upload(p->low.stream_begin, &p->d_stream_begin)) != TRX_OK) return s;
+  if ((s = upload(p->low.const_idx, &p->d_const_idx)) != TRX_OK) return s;
+  if ((s = upload(p->low.const_bits, &p->d_const_bits)) != TRX_OK) return s;
+  for (int which = 0; which < 3; which++) {
+    const trx::PortLayout &L = p->layout(which);
+    std::vector<DevElem> elems(L.elems.size());
+    for (size_t i = 0; i < elems.size(); i++)
+      elems[i] = {L.elems[i].idx, L.elems[i].fixed, L.elems[i].per_lane, L.elems[i].lane};
+    p->n_elems[which] = (uint32_t)elems.size();
+    if ((s = upload(elems, &p->d_elems[which])) != TRX_OK) return s;
+  }
+  *out = p.release();
+  return TRX_OK;
+}
+
+trx_status trx_program_create(const trx_program_desc *d, int device, trx_program **out) {
+  if (!d) return fail(TRX_ERR_INVALID, "null program description");
+  trxfile::Program src;
+  src.memory_size = d->memory_size;
+  src.ops.resize(d->n_ops);
+  for (uint32_t i = 0; i < d->n_ops; i++) {
+    src.ops[i].name = d->ops[i].name ? d->ops[i].name : "";
+    src.ops[i].args.resize(d->ops[i].n_args);
+    for (uint32_t k = 0; k < d->ops[i].n_args; k++) {
+      src.ops[i].args[k].size = d->ops[i].args[k].size;
+      src.ops[i].args[k].is_input = d->ops[i].args[k].is_input;
+      src.ops[i].args[k].lanes = d->ops[i].args[k].lanes;
+      src.ops[i].args[k].elem = d->ops[i].args[k].elem;
+    }
+  }
+  src.n_instructions = d->n_instructions;
+  src.code.assign(d->code, d->code + d->n_code_words);
+  auto ports = [](const trx_port_desc *p, uint32_t n, std::vector<trxfile::Port> &dst) {
+    dst.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+      dst[i].address = p[i].address;
+      dst[i].offset = p[i].offset;
+      dst[i].size = p[i].size;
+      dst[i].lanes = p[i].lanes;
+      dst[i].elem = p[i].elem;
+    }
+  };
+  ports(d->inputs, d->n_inputs, src.inputs);
+  ports(d->parameters, d->n_parameters, src.parameters);
+  ports(d->outputs, d->n_outputs, src.outputs);
+  ports(d->constants, d->n_constants, src.constants);
+  src.const_data.assign(d->const_data, d->const_data + d->n_const_data);
+  return createFromFile(src, device, d->scalar_inputs, d->scalar_outputs, out);
+}
+
+trx_status trx_program_create_from_blob(const void *blob, size_t bytes, int device, trx_program **out) {
+  trxfile::Program src;
+  try {
+    trxfile::decodeProgram(blob, bytes, src);
+  } catch (const std::exception &e) {
+    return fail(TRX_ERR_INVALID, e.what());
+  }
+  return createFromFile(src, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, out);
+}
+
+void trx_program_destroy(trx_program *p) {
+  if (!p) return;
+  cudaFree(p->d_stream);
+  cudaFree(p->d_stream_begin);
+  cudaFree(p->d_const_idx);
+  cudaFree(p->d_const_bits);
+  for (auto *e : p->d_elems) cudaFree(e);
+  delete p;
+}
+
+trx_status trx_program_buffer_bytes(const trx_program *p, int which, uint64_t lanes, uint64_t *bytes) {
+  if (!p || !bytes || which < 0 || which > 2) return fail(TRX_ERR_INVALID, "bad argument");
+  *bytes = p->layout(which).wideElems(lanes) * 8;
+  return TRX_OK;
+}
+
+trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *value) {
+  if (!p || !key || !value) return fail(TRX_ERR_INVALID, "bad argument");
+  std::string k = key;
+  if (k == "n_instructions") *value = p->low.n_instructions;
+  else if (k == "n_levels") *value = p->low.n_levels;
+  else if (k == "n_bundles") *value = p->low.n_bundles;
+  else if (k == "stream_words") *value = p->low.stream.size();
+  else if (k == "memory_size") *value = p->low.memory_size;
+  else if (k == "n_warps") *value = p->low.n_warps;
+  else if (k == "arg_bytes_per_tile") *value = p->low.arg_bytes_per_tile;
+  else if (k == "max_level_width") *value = p->low.max_level_width;
+  else if (k == "n_constants") *value = p->low.const_idx.size();
+  else if (k == "scalar_inputs") *value = (uint64_t)p->scalar_inputs;
+  else if (k == "scalar_outputs") *value = (uint64_t)p->scalar_outputs;
+  else return fail(TRX_ERR_INVALID, "unknown statistic " + k);
+  return TRX_OK;
+}
+
+trx_status trx_memory_create(uint64_t lanes, int device, trx_memory **out) {
+  if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  if (lanes == 0 || lanes % 8 != 0) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TRX_ERR_CUDA, "no CUDA device: the tape engine has no CPU execution path");
+  TRX_CUDA(cudaSetDevice(device));
+  trx_memory *m = new trx_memory();
+  m->device = device;
+  m->lanes = lanes;
+  m->n_tiles = lanes / 8;
+  *out = m;
+  return TRX_OK;
+}
+
+void trx_memory_destroy(trx_memory *m) {
+  if (!m) return;
+  cudaFree(m->d_mem);
+  cudaFree(m->d_stage);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  delete m;
+}
+
+trx_status trx_memory_lanes(const trx_memory *m, uint64_t *lanes) {
+  if (!m || !lanes) return fail(TRX_ERR_INVALID, "bad argument");
+  *lanes = m->lanes;
+  return TRX_OK;
+}
+
+trx_status trx_memory_bytes(const trx_memory *m, uint64_t *bytes) {
+  if (!m || !bytes) return fail(TRX_ERR_INVALID, "bad argument");
+  *bytes = m->tile_stride * m->n_tiles * 8;
+  return TRX_OK;
+}
+
+trx_status trx_input(const trx_program *p, trx_memory *m, const void *packed, uint64_t bytes, void *stream) {
+  if (!p || !m || (!packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(m->device));
+  return scatterHost(p, m, TRX_BUF_INPUT, packed, bytes, (cudaStream_t)stream);
+}
+trx_status trx_parameterize(const trx_program *p, trx_memory *m, const void *packed, uint64_t bytes, void *stream) {
+  if (!p || !m || (!packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(m->device));
+  return scatterHost(p, m, TRX_BUF_PARAMETER, packed, bytes, (cudaStream_t)stream);
+}
+trx_status trx_input_device(const trx_program *p, trx_memory *m, const void *d, uint64_t bytes, void *stream) {
+  if (!p || !m || (!d && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(m->device));
+  return scatterDevice(p, m, TRX_BUF_INPUT, (const double *)d, bytes, (cudaStream_t)stream);
+}
+trx_status trx_parameterize_device(const trx_program *p, trx_memory *m, const void *d, uint64_t bytes, void *stream) {
+  if (!p || !m || (!d && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(m->device));
+  return scatterDevice(p, m, TRX_BUF_PARAMETER, (const double *)d, bytes, (cudaStream_t)stream);
+}
+
+trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
+  if (!p || !m) return fail(TRX_ERR_INVALID, "bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TRX_CUDA(cudaSetDevice(m->device));
+  trx_status s = ensureTileStride(m, p->low.memory_size, stream);
+  if (s != TRX_OK) return s;
+  uint32_t nc = (uint32_t)p->low.const_idx.size();
+  if (nc) {
+    dim3 grid((nc + 255) / 256, (unsigned)m->n_tiles);
+    trx_const_kernel<<<grid, 256, 0, stream>>>(p->d_const_idx, p->d_const_bits, nc, m->d_mem, m->tile_stride);
+    g_launches++;
+  }
+  if (p->low.n_instructions) {
+    uint32_t W = p->low.n_warps;
+    if (W <= 8)
+      trx_vm_kernel<8><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                 m->tile_stride);
+    else if (W <= 16)
+      trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                  m->tile_stride);
+    else
+      trx_vm_kernel<32><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                  m->tile_stride);
+    g_launches++;
+  }
+  TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed, uint64_t bytes, void *stream_) {
+  if (!p || !m || (!d_packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TRX_CUDA(cudaSetDevice(m->device));
+  const trx::PortLayout &L = p->low.outputs;
+  uint64_t expect = L.wideElems(m->lanes) * 8;
+  if (bytes != expect)
+    return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+                                  std::to_string(expect));
+  if (m->tile_stride * 8 < p->low.memory_size)
+    return fail(TRX_ERR_INVALID, "memory has not been written by a program of this size yet");
+  uint32_t n = p->n_elems[TRX_BUF_OUTPUT];
+  if (n == 0) return TRX_OK;
+  dim3 grid((n + 255) / 256, (unsigned)m->n_tiles);
+  trx_gather_kernel<<<grid, 256, 0, stream>>>(p->d_elems[TRX_BUF_OUTPUT], n, (double *)d_packed, m->lanes, m->d_mem,
+                                             m->tile_stride, (uint32_t)m->n_tiles,
+                                             p->scalar_outputs == TRX_SCALAR_REDUCE ? 1 : 0);
+  g_launches++;
+  TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+trx_status trx_output(const trx_program *p, trx_memory *m, void *packed, uint64_t bytes, void *stream_) {
+  if (!p || !m || (!packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TRX_CUDA(cudaSetDevice(m->device));
+  uint64_t elems = p->low.outputs.wideElems(m->lanes);
+  if (bytes != elems * 8)
+    return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+                                  std::to_string(elems * 8));
+  if (elems == 0) return TRX_OK;
+  trx_status s = ensureStage(m, elems, true);
+  if (s != TRX_OK) return s;
+  s = trx_output_device(p, m, m->d_stage, bytes, stream_);
+  if (s != TRX_OK) return s;
+  TRX_CUDA(cudaMemcpyAsync(m->h_stage, m->d_stage, bytes, cudaMemcpyDeviceToHost, stream));
+  TRX_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(packed, m->h_stage, bytes);
+  return TRX_OK;
+}
+
+trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes) {
+  if (!m || !dst) return fail(TRX_ERR_INVALID, "bad argument");
+  if (tile >= m->n_tiles || address + bytes > m->tile_stride * 8) return fail(TRX_ERR_INVALID, "peek out of range");
+  TRX_CUDA(cudaSetDevice(m->device));
+  TRX_CUDA(cudaDeviceSynchronize());
+  TRX_CUDA(cudaMemcpy(dst, (const uint8_t *)m->d_mem + tile * m->tile_stride * 8 + address, bytes,
+                      cudaMemcpyDeviceToHost));
+  return TRX_OK;
+}
+
+}  // extern "C"

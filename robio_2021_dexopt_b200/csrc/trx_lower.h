@@ -1,0 +1,296 @@
+// trx_lower.h -- lowering of a tractor tape to the B200 VM's instruction streams.
+//
+// What the reference does per program in SimpleEngine::_compile
+// (tractor/src/engines/simple.cpp:7-20: flatten to {function pointer, argument
+// base}) becomes here:
+//   1. operator names -> device opcodes, argument layouts verified
+//   2. dependency analysis over byte addresses (RAW / WAR / WAW) -> ASAP levels.
+//      The only engine of the reference that reorders a tape is LoopEngine's
+//      scheduleSimple (tractor/src/engines/loop.cpp:10-39); this is the same
+//      levelisation, extended with WAR/WAW edges because bprop tapes overwrite
+//      gradient slots (tractor/src/core/gradients.cpp:120-179).
+//   3. same-opcode instructions of a level are packed into warp bundles:
+//      4 lane-typed (*_8d) instructions x 8 lanes, or 32 scalar-typed (*_d)
+//      instructions, per 32-thread warp, so a warp never diverges on the opcode
+//   4. bundles are distributed over W per-warp streams (longest-processing-time
+//      first), every level ends with a BARRIER word in every stream
+// plus flat element maps for the port scatter/gather and constant upload
+// kernels (ExecutableBase::_input/_output/_parameterize, src/engines/base.cpp:9-40;
+// constant copy of SimpleEngine::_execute, simple.cpp:27-30).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/trx_file.h"
+#include "trx_ops.h"
+
+namespace trx {
+
+struct HeaderBits {
+  static uint32_t make(uint32_t opcode, bool wide, uint32_t n_sub, uint32_t n_args) {
+    return (opcode & 0x7ffu) | ((wide ? 1u : 0u) << 11) | (((n_sub - 1) & 31u) << 12) | ((n_args & 15u) << 17);
+  }
+};
+
+// The wide layout places ports in order; a lane-typed port occupies comps * R elements.
+// wide_base for element (port p, comp c, lane l) = fixed_before_p + per_lane_before_p * R + c * R + l,
+// so it is stored as (fixed part, per-lane multiplier part) and resolved when R is known.
+struct PortLayout {
+  struct Elem {
+    uint32_t idx;
+    uint32_t fixed;     // scalar elements before this one
+    uint32_t per_lane;  // lane-typed components before this one (multiplied by R)
+    uint8_t lane;       // lane inside the tile (0..7) or 0xff for scalar-typed
+  };
+  std::vector<Elem> elems;
+  uint64_t fixed_total = 0, per_lane_total = 0;
+  uint64_t wideElems(uint64_t lanes) const { return fixed_total + per_lane_total * lanes; }
+};
+
+inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32_t lane_width) {
+  PortLayout L;
+  uint64_t fixed = 0, per_lane = 0;
+  for (auto &p : ports) {
+    if (p.address % 8 || p.size % 8) throw std::runtime_error("port not 8-byte aligned");
+    if (p.lanes == 1) {
+      uint32_t n = p.size / 8;
+      for (uint32_t c = 0; c < n; c++)
+        L.elems.push_back({(uint32_t)(p.address / 8 + c), (uint32_t)(fixed + c), (uint32_t)per_lane, 0xff});
+      fixed += n;
+    } else {
+      if (p.lanes != lane_width) throw std::runtime_error("port lane width differs from the tape's lane width");
+      uint32_t comps = p.size / (8 * p.lanes);
+      for (uint32_t c = 0; c < comps; c++)
+        for (uint32_t l = 0; l < p.lanes; l++)
+          L.elems.push_back({(uint32_t)(p.address / 8 + c * p.lanes + l), (uint32_t)fixed, (uint32_t)(per_lane + c),
+                             (uint8_t)l});
+      per_lane += comps;
+    }
+  }
+  L.fixed_total = fixed;
+  L.per_lane_total = per_lane;
+  return L;
+}
+
+struct LowerOptions {
+  uint32_t n_warps = 8;
+};
+
+struct LoweredProgram {
+  uint64_t memory_size = 0;
+  uint32_t lane_width = 8;
+  uint32_t n_warps = 8;
+  std::vector<uint32_t> stream;
+  std::vector<uint64_t> stream_begin;
+  uint64_t n_instructions = 0, n_levels = 0, n_bundles = 0;
+  uint64_t arg_bytes_per_tile = 0;
+  uint64_t max_level_width = 0;
+  bool has_forward = false, has_reverse = false;
+  PortLayout inputs, parameters, outputs;
+  std::vector<uint32_t> const_idx;
+  std::vector<uint64_t> const_bits;
+};
+
+inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, LoweredProgram &out) {
+  const auto &table = opTable();
+  out = LoweredProgram();
+  out.memory_size = (src.memory_size + 255) / 256 * 256;
+  out.n_warps = opt.n_warps;
+  if (opt.n_warps < 1 || opt.n_warps > 32) throw std::runtime_error("n_warps out of range");
+  if (src.memory_size / 8 >= 0xffffffffull) throw std::runtime_error("memory image too large for 32-bit slot indices");
+
+  // ---- 1. operator table -> opcodes, signature check
+  struct OpRef {
+    uint16_t opcode;
+    uint32_t lane_width;
+  };
+  std::vector<OpRef> ops(src.ops.size());
+  uint32_t tape_lanes = 1;
+  for (size_t i = 0; i < src.ops.size(); i++) {
+    const auto &d = src.ops[i];
+    uint16_t opcode;
+    uint32_t lw;
+    if (!findOp(d.name, opcode, lw))
+      throw std::runtime_error("unsupported operator on the device engine (no CPU fallback): " + d.name);
+    const OpSig &sig = table[opcode];
+    if (sig.args.size() != d.args.size())
+      throw std::runtime_error("argument count mismatch for " + d.name);
+    for (size_t k = 0; k < d.args.size(); k++) {
+      const ArgSig &a = sig.args[k];
+      uint32_t expect_lanes = (a.kind == ARG_T) ? lw : 1;
+      uint32_t expect_size = a.comps * 8 * expect_lanes;
+      if (d.args[k].size != expect_size || (d.args[k].is_input != 0) != a.is_input || d.args[k].lanes != expect_lanes)
+        throw std::runtime_error("argument layout mismatch for " + d.name + " arg " + std::to_string(k));
+    }
+    ops[i] = {opcode, lw};
+    tape_lanes = std::max(tape_lanes, lw);
+    if (sig.mode == 'F') out.has_forward = true;
+    if (sig.mode == 'R') out.has_reverse = true;
+  }
+  for (auto *ports : {&src.inputs, &src.parameters, &src.outputs, &src.constants})
+    for (auto &p : *ports) tape_lanes = std::max<uint32_t>(tape_lanes, p.lanes);
+  if (tape_lanes != 1 && tape_lanes != 8) throw std::runtime_error("only Batch<double,8> lane tapes are supported");
+  out.lane_width = 8;  // scalar-only tapes still run on 8-lane tiles (lane 0 active)
+
+  // ---- 2. decode instructions
+  struct Inst {
+    uint32_t op;      // index into ops
+    uint64_t code_at; // position of the first argument in src.code
+    uint32_t level;
+  };
+  std::vector<Inst> insts;
+  insts.reserve(src.n_instructions);
+  {
+    uint64_t pc = 0;
+    while (pc < src.code.size()) {
+      uint64_t oi = src.code[pc];
+      if (oi >= ops.size()) throw std::runtime_error("invalid op");  // engine.cpp:44-48
+      size_t na = table[ops[oi].opcode].args.size();
+      if (pc + 1 + na > src.code.size()) throw std::runtime_error("truncated instruction");
+      insts.push_back({(uint32_t)oi, pc + 1, 0});
+      pc += 1 + na;
+    }
+    if (insts.size() != src.n_instructions) throw std::runtime_error("instruction count mismatch");
+  }
+  out.n_instructions = insts.size();
+
+  // ---- 3. levels (ASAP) with RAW / WAR / WAW edges keyed by argument start address
+  std::vector<uint64_t> addrs;
+  addrs.reserve(src.code.size());
+  for (auto &in : insts) {
+    size_t na = table[ops[in.op].opcode].args.size();
+    for (size_t k = 0; k < na; k++) {
+      uint64_t a = src.code[in.code_at + k];
+      if (a % 8) throw std::runtime_error("argument address not 8-byte aligned");
+      if (a >= src.memory_size) throw std::runtime_error("argument address outside the memory image");
+      addrs.push_back(a);
+    }
+  }
+  std::sort(addrs.begin(), addrs.end());
+  addrs.erase(std::unique(addrs.begin(), addrs.end()), addrs.end());
+  auto slotId = [&](uint64_t a) -> size_t {
+    return (size_t)(std::lower_bound(addrs.begin(), addrs.end(), a) - addrs.begin());
+  };
+  std::vector<uint32_t> wlevel(addrs.size(), 0), rlevel(addrs.size(), 0);
+  uint32_t n_levels = 0;
+  std::vector<size_t> ids;
+  for (auto &in : insts) {
+    const OpSig &sig = table[ops[in.op].opcode];
+    size_t na = sig.args.size();
+    ids.resize(na);
+    uint32_t lvl = 0;
+    uint32_t lw = ops[in.op].lane_width;
+    for (size_t k = 0; k < na; k++) {
+      ids[k] = slotId(src.code[in.code_at + k]);
+      if (sig.args[k].is_input) lvl = std::max(lvl, wlevel[ids[k]]);
+      else lvl = std::max(lvl, std::max(wlevel[ids[k]], rlevel[ids[k]]));
+      out.arg_bytes_per_tile += (uint64_t)sig.args[k].comps * 8 * (sig.args[k].kind == ARG_T ? lw : 1);
+    }
+    in.level = lvl + 1;
+    n_levels = std::max(n_levels, in.level);
+    for (size_t k = 0; k < na; k++)
+      if (sig.args[k].is_input) rlevel[ids[k]] = std::max(rlevel[ids[k]], in.level);
+    for (size_t k = 0; k < na; k++)
+      if (!sig.args[k].is_input) {
+        wlevel[ids[k]] = in.level;
+        rlevel[ids[k]] = in.level;
+      }
+  }
+  out.n_levels = n_levels;
+
+  // ---- 4. bucket by level, then by (opcode, width), build bundles, distribute to warps
+  std::vector<uint32_t> level_count(n_levels + 2, 0);
+  for (auto &in : insts) level_count[in.level + 1]++;
+  for (size_t l = 1; l < level_count.size(); l++) level_count[l] += level_count[l - 1];
+  std::vector<uint32_t> order(insts.size());
+  {
+    std::vector<uint32_t> fill(level_count.begin(), level_count.end());
+    for (uint32_t i = 0; i < insts.size(); i++) order[fill[insts[i].level]++] = i;
+  }
+  const uint32_t W = opt.n_warps;
+  std::vector<std::vector<uint32_t>> streams(W);
+  struct Bundle {
+    uint16_t opcode;
+    bool wide;
+    uint32_t first, count;  // range in the level's sorted list
+    uint32_t cost;
+  };
+  std::vector<uint32_t> lvl_insts;
+  std::vector<Bundle> bundles;
+  std::vector<uint64_t> load(W);
+  for (uint32_t level = 1; level <= n_levels; level++) {
+    lvl_insts.assign(order.begin() + level_count[level], order.begin() + level_count[level + 1]);
+    out.max_level_width = std::max<uint64_t>(out.max_level_width, lvl_insts.size());
+    std::stable_sort(lvl_insts.begin(), lvl_insts.end(), [&](uint32_t a, uint32_t b) {
+      const OpRef &oa = ops[insts[a].op], &ob = ops[insts[b].op];
+      if (oa.opcode != ob.opcode) return oa.opcode < ob.opcode;
+      return oa.lane_width < ob.lane_width;
+    });
+    bundles.clear();
+    for (size_t i = 0; i < lvl_insts.size();) {
+      const OpRef &o = ops[insts[lvl_insts[i]].op];
+      bool wide = (o.lane_width == 1);
+      uint32_t cap = wide ? 32 : 4;
+      size_t j = i;
+      while (j < lvl_insts.size() && j - i < cap) {
+        const OpRef &o2 = ops[insts[lvl_insts[j]].op];
+        if (o2.opcode != o.opcode || o2.lane_width != o.lane_width) break;
+        j++;
+      }
+      bundles.push_back({o.opcode, wide, (uint32_t)i, (uint32_t)(j - i), table[o.opcode].cost + 8});
+      i = j;
+    }
+    out.n_bundles += bundles.size();
+    std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle &a, const Bundle &b) { return a.cost > b.cost; });
+    std::fill(load.begin(), load.end(), 0);
+    for (auto &bd : bundles) {
+      uint32_t w = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[w] += bd.cost;
+      auto &s = streams[w];
+      const OpSig &sig = table[bd.opcode];
+      uint32_t na = (uint32_t)sig.args.size();
+      uint32_t stride = bd.wide ? 32 : 4;
+      s.push_back(HeaderBits::make(bd.opcode, bd.wide, bd.count, na));
+      size_t base = s.size();
+      s.resize(base + (size_t)na * stride, 0);
+      for (uint32_t i = 0; i < bd.count; i++) {
+        const Inst &in = insts[lvl_insts[bd.first + i]];
+        for (uint32_t k = 0; k < na; k++) s[base + (size_t)k * stride + i] = (uint32_t)(src.code[in.code_at + k] / 8);
+      }
+      // idle sub-slots repeat the first instruction's addresses so that address arithmetic stays in range
+      for (uint32_t i = bd.count; i < stride; i++)
+        for (uint32_t k = 0; k < na; k++) s[base + (size_t)k * stride + i] = s[base + (size_t)k * stride];
+    }
+    for (auto &s : streams) s.push_back(HeaderBits::make(OP_BARRIER, false, 1, 0));
+  }
+  for (auto &s : streams) s.push_back(HeaderBits::make(OP_END, false, 1, 0));
+  out.stream_begin.assign(W + 1, 0);
+  for (uint32_t w = 0; w < W; w++) {
+    out.stream_begin[w] = out.stream.size();
+    out.stream.insert(out.stream.end(), streams[w].begin(), streams[w].end());
+    // pad so that a one-record look-ahead never reads past the allocation
+    for (int i = 0; i < 16; i++) out.stream.push_back(HeaderBits::make(OP_END, false, 1, 0));
+  }
+  out.stream_begin[W] = out.stream.size();
+
+  // ---- 5. ports and constants
+  out.inputs = makePortLayout(src.inputs, tape_lanes == 1 ? 8 : tape_lanes);
+  out.parameters = makePortLayout(src.parameters, tape_lanes == 1 ? 8 : tape_lanes);
+  out.outputs = makePortLayout(src.outputs, tape_lanes == 1 ? 8 : tape_lanes);
+  for (auto &p : src.constants) {
+    if (p.address % 8 || p.size % 8) throw std::runtime_error("constant not 8-byte aligned");
+    if (p.offset + p.size > src.const_data.size()) throw std::runtime_error("constant outside the constant blob");
+    if (p.address + p.size > src.memory_size) throw std::runtime_error("constant outside the memory image");
+    for (uint32_t e = 0; e < p.size / 8; e++) {
+      uint64_t bits;
+      std::memcpy(&bits, src.const_data.data() + p.offset + (size_t)e * 8, 8);
+      out.const_idx.push_back((uint32_t)(p.address / 8 + e));
+      out.const_bits.push_back(bits);
+    }
+  }
+}
+
+}  // namespace trx

@@ -1,0 +1,195 @@
+// vm_emu.cpp -- TEST-ONLY host emulation of the B200 tape VM.
+//
+// Compiles the *same* lowering (csrc/trx_lower.h) and the *same* operator bodies
+// (csrc/vm_ops.def through csrc/vm_exec.cuh, built as plain C++) into a small
+// shared object that walks the per-warp instruction streams sequentially.  It
+// exists so that the CPU test suite (pytest -m "not gpu") can check the
+// lowering (levels, bundles, port maps) and every operator body against the
+// reference's golden vectors without a GPU.  It is NOT part of the product:
+// nothing in robio_2021_dexopt_b200/ loads it, libtrx_b200.so has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/trx_b200.h"
+#include "../../robio_2021_dexopt_b200/csrc/trx_lower.h"
+#include "../../robio_2021_dexopt_b200/csrc/vm_exec.cuh"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string &m) {
+  g_err = m;
+  return code;
+}
+}  // namespace
+
+struct emu_program {
+  trx::LoweredProgram low;
+  int scalar_inputs, scalar_outputs;
+  const trx::PortLayout &layout(int which) const {
+    return which == TRX_BUF_INPUT ? low.inputs : which == TRX_BUF_PARAMETER ? low.parameters : low.outputs;
+  }
+};
+struct emu_memory {
+  uint64_t lanes, n_tiles, tile_stride = 0;  // doubles
+  std::vector<double> mem;
+  void ensure(uint64_t bytes) {
+    uint64_t need = (bytes + 255) / 256 * 256 / 8;
+    if (need <= tile_stride) return;
+    std::vector<double> fresh(need * n_tiles, 0.0);
+    for (uint64_t t = 0; t < n_tiles; t++)
+      std::memcpy(fresh.data() + t * need, mem.data() + t * tile_stride, tile_stride * 8);
+    mem.swap(fresh);
+    tile_stride = need;
+  }
+};
+
+extern "C" {
+const char *emu_last_error(void) { return g_err.c_str(); }
+
+int emu_program_create_from_blob(const void *blob, size_t bytes, int warps, emu_program **out) {
+  *out = nullptr;
+  try {
+    trxfile::Program src;
+    trxfile::decodeProgram(blob, bytes, src);
+    std::unique_ptr<emu_program> p(new emu_program());
+    trx::LowerOptions opt;
+    opt.n_warps = (uint32_t)warps;
+    trx::lowerProgram(src, opt, p->low);
+    bool reverse_only = p->low.has_reverse && !p->low.has_forward;
+    p->scalar_inputs = reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED;
+    p->scalar_outputs = p->low.has_reverse ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED;
+    *out = p.release();
+    return TRX_OK;
+  } catch (const std::exception &e) {
+    std::string m = e.what();
+    return fail(m.find("unsupported operator") != std::string::npos ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, m);
+  }
+}
+void emu_program_destroy(emu_program *p) { delete p; }
+int emu_program_buffer_bytes(const emu_program *p, int which, uint64_t lanes, uint64_t *bytes) {
+  *bytes = p->layout(which).wideElems(lanes) * 8;
+  return TRX_OK;
+}
+int emu_program_stat(const emu_program *p, const char *key, uint64_t *value) {
+  std::string k = key;
+  if (k == "n_instructions") *value = p->low.n_instructions;
+  else if (k == "n_levels") *value = p->low.n_levels;
+  else if (k == "n_bundles") *value = p->low.n_bundles;
+  else if (k == "stream_words") *value = p->low.stream.size();
+  else if (k == "memory_size") *value = p->low.memory_size;
+  else if (k == "max_level_width") *value = p->low.max_level_width;
+  else if (k == "arg_bytes_per_tile") *value = p->low.arg_bytes_per_tile;
+  else return fail(TRX_ERR_INVALID, "unknown statistic");
+  return TRX_OK;
+}
+int emu_memory_create(uint64_t lanes, emu_memory **out) {
+  if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
+  auto *m = new emu_memory();
+  m->lanes = lanes;
+  m->n_tiles = lanes / 8;
+  *out = m;
+  return TRX_OK;
+}
+void emu_memory_destroy(emu_memory *m) { delete m; }
+
+static int scatter(const emu_program *p, emu_memory *m, int which, const double *wide, uint64_t bytes) {
+  const trx::PortLayout &L = p->layout(which);
+  if (bytes != L.wideElems(m->lanes) * 8) return fail(TRX_ERR_SIZE, "packed buffer size mismatch");
+  m->ensure(p->low.memory_size);
+  bool once = which == TRX_BUF_INPUT && p->scalar_inputs == TRX_SCALAR_REDUCE;
+  for (uint64_t t = 0; t < m->n_tiles; t++)
+    for (auto &e : L.elems) {
+      double v;
+      if (e.lane == 0xff) {
+        v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * m->lanes];
+        if (once && t != 0) v = 0.0;
+      } else {
+        v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * m->lanes + t * 8 + e.lane];
+      }
+      m->mem[t * m->tile_stride + e.idx] = v;
+    }
+  return TRX_OK;
+}
+int emu_input(const emu_program *p, emu_memory *m, const void *packed, uint64_t bytes) {
+  return scatter(p, m, TRX_BUF_INPUT, (const double *)packed, bytes);
+}
+int emu_parameterize(const emu_program *p, emu_memory *m, const void *packed, uint64_t bytes) {
+  return scatter(p, m, TRX_BUF_PARAMETER, (const double *)packed, bytes);
+}
+int emu_output(const emu_program *p, emu_memory *m, void *packed, uint64_t bytes) {
+  const trx::PortLayout &L = p->low.outputs;
+  if (bytes != L.wideElems(m->lanes) * 8) return fail(TRX_ERR_SIZE, "packed buffer size mismatch");
+  double *wide = (double *)packed;
+  bool sum = p->scalar_outputs == TRX_SCALAR_REDUCE;
+  for (uint64_t t = 0; t < m->n_tiles; t++)
+    for (auto &e : L.elems) {
+      if (e.lane == 0xff) {
+        if (t != 0) continue;
+        double v = m->mem[e.idx];
+        if (sum)
+          for (uint64_t u = 1; u < m->n_tiles; u++) v += m->mem[u * m->tile_stride + e.idx];
+        wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * m->lanes] = v;
+      } else {
+        wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * m->lanes + t * 8 + e.lane] = m->mem[t * m->tile_stride + e.idx];
+      }
+    }
+  return TRX_OK;
+}
+
+// Walks the W streams level by level, the warps of a level one after the other and the
+// 32 threads of a warp in turn -- any valid schedule must give the same answer.
+int emu_execute(const emu_program *p, emu_memory *m) {
+  m->ensure(p->low.memory_size);
+  const auto &low = p->low;
+  for (uint64_t t = 0; t < m->n_tiles; t++) {
+    double *mem = m->mem.data() + t * m->tile_stride;
+    for (size_t i = 0; i < low.const_idx.size(); i++) std::memcpy(mem + low.const_idx[i], &low.const_bits[i], 8);
+    uint32_t W = low.n_warps;
+    std::vector<const uint32_t *> pc(W);
+    for (uint32_t w = 0; w < W; w++) pc[w] = low.stream.data() + low.stream_begin[w];
+    bool done = false;
+    while (!done) {
+      for (uint32_t w = 0; w < W; w++) {
+        while (true) {
+          uint32_t hdr = *pc[w];
+          uint32_t op = hdr & 0x7ffu;
+          if (op == trx::OP_END) {
+            done = true;
+            break;
+          }
+          if (op == trx::OP_BARRIER) {
+            pc[w]++;
+            break;
+          }
+          bool wide = (hdr >> 11) & 1u;
+          int nsub = (int)((hdr >> 12) & 31u) + 1;
+          int nargs = (int)((hdr >> 17) & 15u);
+          for (int lane32 = 0; lane32 < 32; lane32++) {
+            trxvm::Ctx c;
+            c.m = mem;
+            int sub;
+            if (wide) {
+              sub = lane32;
+              c.as = 32;
+              c.cs = 1;
+              c.lo = 0;
+            } else {
+              sub = lane32 >> 3;
+              c.as = 4;
+              c.cs = 8;
+              c.lo = lane32 & 7;
+            }
+            c.a = pc[w] + 1 + sub;
+            if (sub < nsub) trxvm::exec(op, c);
+          }
+          pc[w] += 1 + nargs * (wide ? 32 : 4);
+        }
+      }
+    }
+  }
+  return TRX_OK;
+}
+}

@@ -1,0 +1,133 @@
+"""GPU suite: the CUDA engine, called through the C ABI (include/trx_b200.h), against the
+reference SimpleEngine's golden vectors.  Same checks as the CPU suite runs on the emulation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- no GPU needed
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from robio_2021_dexopt_b200 import _native
+    L = _native.lib()
+    header = open(os.path.join(ROOT, "include", "trx_b200.h")).read()
+    names = set(re.findall(r"\b(trx_[a-z_]+)\s*\(", header))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(L, n), "libtrx_b200.so does not export %s" % n
+
+
+def test_operator_vocabulary_matches_reference_registry():
+    """every device operator's argument layout equals what Operator::arguments() reports
+    (tests/golden/ref_registry.txt, dumped from the reference's registry)"""
+    from robio_2021_dexopt_b200 import _native
+    L = _native.lib()
+    ref = {}
+    for line in open(os.path.join(ROOT, "tests", "golden", "ref_registry.txt")):
+        parts = line.split()
+        ref[parts[0]] = parts[3:]
+    checked = 0
+    for i in range(L.trx_op_count()):
+        name = L.trx_op_name(i).decode()
+        sig = L.trx_op_signature(i).decode().split()
+        for suffix, lanes in (("_8d", 8), ("_d", 1)):
+            full = name + suffix
+            assert full in ref, "device operator %s is not a reference operator" % full
+            want = ref[full]
+            assert len(want) == len(sig), full
+            for tok, w in zip(sig, want):
+                size, io, wl, elem = w.split(":")
+                comps = int(tok[2:])
+                arg_lanes = lanes if tok[1] == "T" else 1
+                assert int(size) == comps * 8 * arg_lanes, (full, tok, w)
+                assert io == tok[0], (full, tok, w)
+                assert int(wl) == arg_lanes, (full, tok, w)
+            checked += 1
+    assert checked >= 500
+
+
+def test_no_device_means_error_not_fallback():
+    from robio_2021_dexopt_b200 import _native
+    L = _native.lib()
+    if L.trx_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = ctypes.c_void_p()
+    st = L.trx_memory_create(8, 0, ctypes.byref(h))
+    assert st == -3 and b"no CPU" in L.trx_last_error()
+
+
+def test_uncompiled_executable_raises_like_the_reference():
+    import robio_2021_dexopt_b200 as pkg
+    x = pkg.Executable()
+    with pytest.raises(RuntimeError, match=r"call compile\(\.\.\.\) before use"):
+        x.execute(None)
+
+
+# ---------------------------------------------------------------- GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["optests_8d.trxb", "optests_d.trxb"])
+def test_every_operator_matches_reference(cuda_engine, golden, fixture):
+    bundle = golden(fixture)
+    for name, grad in parity.op_names(bundle):
+        parity.check_single_op(cuda_engine, bundle, name, grad == "grad")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,tiles", [("fkchain24.trxb", 2), ("fkchain24.trxb", 1),
+                                          ("dexsyn_small.trxb.xz", 2), ("dexsyn_dropout_outer2.trxb.xz", 2)])
+def test_problem_parity(cuda_engine, golden, fixture, tiles):
+    parity.check_problem(cuda_engine, golden(fixture), n_tiles=tiles)
+
+
+@pytest.mark.gpu
+def test_unsupported_operator_is_a_hard_error(cuda_engine, golden):
+    import robio_2021_dexopt_b200 as pkg
+    blob = golden("optests_8d.trxb").programs["op/tanh_8d/prog"]
+    bad = blob.replace(b"tanh_8d", b"tanq_8d")
+    with pytest.raises(pkg.TrxError) as e:
+        cuda_engine.compile(bad)
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_many_tiles_replicate_the_reference_tile(cuda_engine, golden):
+    """size-independent property: R lanes built from copies of one reference tile give R/8 copies of
+    that tile's residuals, and a gradient equal to (lane part) * R/8 + (scalar part) once"""
+    from robio_2021_dexopt_b200 import trxfile
+    bundle = golden("dexsyn_small.trxb.xz")
+    prog, tiles = bundle.view("prog"), 37
+    params = [bundle.arrays["tile0/params"]] * tiles
+    x_prog = cuda_engine.compile(bundle.programs["prog"])
+    x_prep = cuda_engine.compile(bundle.programs["prep"])
+    x_bprop = cuda_engine.compile(bundle.programs["bprop"])
+    mem = cuda_engine.createMemory(8 * tiles)
+    x_prog.parameterize(trxfile.tiles_to_wide(prog.parameters, params), mem)
+    r = x_prog.run(bundle.arrays["x"], mem)
+    per_tile = trxfile.wide_to_tiles(prog.outputs, r, tiles)
+    for t in range(tiles):
+        parity.assert_close(per_tile[t], bundle.arrays["tile0/r"], "tile %d residuals" % t)
+    x_prep.execute(mem)
+    g = x_bprop.run(r, mem)
+    # gradient of tile 0 alone, with and without the scalar-typed residual rows
+    mem1 = cuda_engine.createMemory(8)
+    x_prog.parameterize(trxfile.tiles_to_wide(prog.parameters, params[:1]), mem1)
+    r1 = x_prog.run(bundle.arrays["x"], mem1)
+    x_prep.execute(mem1)
+    g_full = x_bprop.run(r1, mem1)
+    r1_lane = r1.copy()
+    off = 0
+    for p in prog.outputs:
+        n = p.size // 8
+        if p.lanes == 1:
+            r1_lane[off:off + n] = 0
+        off += n
+    g_lane = x_bprop.run(r1_lane, mem1)
+    parity.assert_close(g, g_lane * tiles + (g_full - g_lane), "gradient over %d tiles" % tiles, rtol=1e-10)
