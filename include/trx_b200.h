@@ -167,6 +167,20 @@ uint64_t trx_kernel_launch_count(void);
 /* debug: copy `bytes` of tile `tile`'s memory image starting at byte `address` to the host */
 trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes);
 
+/* ---- objective assembly (product-side recorder) ------------------------------
+ * Stands where dexopt records its problem onto a tape: DexLearn::build ->
+ * Program([&]{ _runTraining(); }) (dexopt/src/dexlearn.h:440-453,511-518) followed by
+ * SolverBase::_compileGradients -> buildGradients (tractor/include/tractor/solvers/base.h:112-138,
+ * tractor/src/core/gradients.cpp:22-407).  Builds the synthetic Shadow-hand rollout problem
+ * (csrc/assembly) with the product's own tape recorder and differentiates it.
+ * `options`: space separated key=value pairs: kind=handarm|hand8|chain frames=T outer=N hidden=H
+ * dropout=0|1 seed=N joints=N contacts=N extra_fixed=N wstd=S.
+ * On success *bundle is a malloc'ed TRXB bundle (include/trx_file.h) holding programs
+ * prog/prep/fprop/bprop/hprop/accu, the array "x" (initial policy parameters) and text "meta". */
+int trx_dexsyn_build(const char *options, uint8_t **bundle, uint64_t *bundle_bytes);
+void trx_builder_free(uint8_t *bundle);
+const char *trx_builder_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,3 +8,4 @@ Only what the path needs lives here:
 from .engine import CudaEngine, Executable, Memory, kernel_launch_count  # noqa: F401
 from ._native import TrxError  # noqa: F401
 from . import trxfile  # noqa: F401
+from .builder import build_dexsyn  # noqa: F401

@@ -53,6 +53,10 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
     L.trx_execute.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     L.trx_memory_peek.argtypes = [c.c_void_p, c.c_uint64, c.c_uint64, c.c_void_p, c.c_uint64]
+    L.trx_dexsyn_build.argtypes = [c.c_char_p, c.POINTER(c.POINTER(c.c_uint8)), c.POINTER(c.c_uint64)]
+    L.trx_builder_free.argtypes = [c.POINTER(c.c_uint8)]
+    L.trx_builder_free.restype = None
+    L.trx_builder_last_error.restype = c.c_char_p
     _lib = L
     return L
 

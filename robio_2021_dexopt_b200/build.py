@@ -43,7 +43,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "trx_engine.cu"), "-o", OUT + ".tmp"]
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "trx_engine.cu"), os.path.join(CSRC, "trx_builder.cpp"),
+                                 "-o", OUT + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

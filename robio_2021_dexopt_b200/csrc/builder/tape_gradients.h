@@ -1,0 +1,283 @@
+// tape_gradients.h -- reverse/forward-mode program derivation by tape rewriting.
+//
+// Product-side restatement of tractor's buildGradients
+// (tractor/src/core/gradients.cpp:22-407) on the neutral program form, so that the
+// product can differentiate tapes it built itself.  Given a forward program it derives
+//   prep   per-instruction linearisation state            gradients.cpp:35-65
+//   bprop  the adjoint sweep, g_in = J^T g_out             gradients.cpp:67-234
+//          (reverse variants in reverse order, fan-out accumulation through
+//          temp + move/add pairs :120-179, zero prologue :205-233)
+//   fprop  the tangent sweep                               gradients.cpp:236-316
+//   hprop  fprop followed by bprop                         gradients.cpp:344-362
+//   accu   x (+) delta per input                           gradients.cpp:364-406
+// Addressing follows the reference: prep state is allocated above the forward image,
+// the gradient slot of forward address a is a + prep.memory_size.
+// Parity is checked program-for-program against the reference's own output in
+// tests/test_builder.py.
+#pragma once
+#include "tape_passes.h"
+
+namespace trxb {
+
+struct Alloc {
+  uint64_t top = 32;  // allocator.h:19
+  uint64_t alloc(uint32_t size, uint32_t lanes) {
+    uint64_t align = (lanes > 1) ? 32 : 8;  // alignas(32) Batch (batch.h:42), natural alignment for double
+    while (top % align) top++;
+    uint64_t r = top;
+    top += size;
+    return r;
+  }
+};
+
+struct GradientPrograms {
+  trxfile::Program prep, fprop, bprop, hprop, accu;
+};
+
+inline std::string variantName(const std::string &name, const char *mode) { return std::string(mode) + "_" + name; }
+inline bool hasOp(const std::string &name) {
+  uint16_t opcode;
+  uint32_t lw;
+  return trx::findOp(name, opcode, lw);
+}
+
+inline std::string typedOp(const char *base, const trxfile::ArgDesc &a) {
+  // compute-mode move/add/zero operator for a value with this layout (Operator::find<compute, op_move>(type))
+  uint32_t comps = a.size / (8 * a.lanes);
+  const char *group = comps == 1 ? "" : comps == 3 ? "_fg_vec3" : comps == 4 ? "_fg_quat" : comps == 6 ? "_fg_twist"
+                      : comps == 7 ? "_fg_pose" : comps == 9 ? "_fg_mat3" : nullptr;
+  if (!group) throw std::runtime_error("no typed operator for a value of " + std::to_string(comps) + " components");
+  return std::string(base) + group + (a.lanes == 8 ? "_8d" : "_d");
+}
+
+inline void packOffsets(std::vector<trxfile::Port> &ports) {
+  uint64_t off = 0;
+  for (auto &p : ports) {
+    p.offset = off;
+    off += p.size;
+  }
+}
+
+inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
+  auto insts = decode(src);
+  out = GradientPrograms();
+  trxfile::Program &prep = out.prep, &fprop = out.fprop, &bprop = out.bprop, &hprop = out.hprop, &accu = out.accu;
+  for (auto *p : {&prep, &fprop, &bprop, &hprop, &accu}) p->lane_width = src.lane_width;
+
+  // ---- prep (gradients.cpp:35-65)
+  std::vector<int64_t> prep_at(insts.size(), -1);  // position of the prepare instruction's first arg in prep.code
+  std::vector<uint32_t> prep_nargs(insts.size(), 0);
+  {
+    Alloc alloc;
+    alloc.top = src.memory_size;
+    auto index = opIndex(prep);
+    for (size_t i = 0; i < insts.size(); i++) {
+      const auto &in = insts[i];
+      std::string pname = variantName(src.ops[in.op].name, "prepare");
+      if (!hasOp(pname)) continue;
+      uint32_t id = internOp(prep, index, pname);
+      const auto &pop = prep.ops[id];
+      prep.code.push_back(id);
+      prep_at[i] = (int64_t)prep.code.size();
+      prep_nargs[i] = (uint32_t)pop.args.size();
+      for (uint32_t k = 0; k < in.n_args; k++) prep.code.push_back(src.code[in.code_at + k]);
+      for (uint32_t k = in.n_args; k < pop.args.size(); k++) prep.code.push_back(alloc.alloc(pop.args[k].size, pop.args[k].lanes));
+      prep.n_instructions++;
+    }
+    prep.memory_size = alloc.top;
+  }
+  const uint64_t G = prep.memory_size;  // gradient slot offset
+
+  // ---- bprop (gradients.cpp:67-234)
+  {
+    for (auto p : src.inputs) {
+      p.address += G;
+      bprop.outputs.push_back(p);
+    }
+    packOffsets(bprop.outputs);
+    for (auto p : src.outputs) {
+      p.address += G;
+      bprop.inputs.push_back(p);
+    }
+    packOffsets(bprop.inputs);
+    auto index = opIndex(bprop);
+    struct RInst {
+      uint32_t op;
+      std::vector<uint64_t> args;
+    };
+    std::vector<RInst> rev;
+    rev.reserve(insts.size());
+    for (size_t i = insts.size(); i-- > 0;) {
+      const auto &in = insts[i];
+      std::string rname = variantName(src.ops[in.op].name, "reverse");
+      if (!hasOp(rname)) throw std::runtime_error("variant not found: reverse " + src.ops[in.op].name);
+      RInst r;
+      r.op = internOp(bprop, index, rname);
+      if (prep_at[i] < 0) {
+        for (uint32_t k = 0; k < in.n_args; k++) r.args.push_back(src.code[in.code_at + k]);
+      } else {
+        for (uint32_t k = in.n_args; k < prep_nargs[i]; k++) r.args.push_back(prep.code[prep_at[i] + k]);
+      }
+      for (uint32_t k = 0; k < in.n_args; k++) r.args.push_back(src.code[in.code_at + k] + G);
+      if (r.args.size() != bprop.ops[r.op].args.size())
+        throw std::runtime_error("reverse signature mismatch for " + src.ops[in.op].name);
+      rev.push_back(std::move(r));
+    }
+    // fan-out accumulation (gradients.cpp:120-179)
+    Alloc alloc;
+    alloc.top = src.memory_size + prep.memory_size;
+    std::unordered_set<uint64_t> written;
+    std::vector<RInst> acc;
+    acc.reserve(rev.size() * 2);
+    for (auto &r : rev) {
+      const auto &op = bprop.ops[r.op];
+      RInst main = r;
+      std::vector<RInst> sums;
+      for (size_t k = 0; k < r.args.size(); k++) {
+        if (op.args[k].is_input) continue;
+        if (written.count(r.args[k])) {
+          uint64_t a = alloc.alloc(op.args[k].size, op.args[k].lanes);
+          uint64_t b = alloc.alloc(op.args[k].size, op.args[k].lanes);
+          RInst mv;
+          mv.op = internOp(bprop, index, typedOp("move", op.args[k]));
+          mv.args = {r.args[k], b};
+          RInst ad;
+          ad.op = internOp(bprop, index, typedOp("add", op.args[k]));
+          ad.args = {b, a, r.args[k]};
+          sums.push_back(mv);
+          sums.push_back(ad);
+          main.args[k] = a;
+        }
+        written.insert(r.args[k]);
+      }
+      acc.push_back(std::move(main));
+      for (auto &s : sums) acc.push_back(std::move(s));
+    }
+    bprop.memory_size = alloc.top;
+    // zero prologue for gradient slots that are read before they are written (gradients.cpp:205-233)
+    std::unordered_set<uint64_t> seen;
+    for (auto &p : bprop.inputs) seen.insert(p.address);
+    std::vector<RInst> zeros;
+    for (auto &r : acc) {
+      const auto &op = bprop.ops[r.op];
+      for (size_t k = 0; k < r.args.size(); k++) {
+        if (r.args[k] < G) continue;
+        if (seen.insert(r.args[k]).second && op.args[k].is_input) {
+          RInst z;
+          // note: op is re-fetched after internOp may have grown the table
+          trxfile::ArgDesc ad = op.args[k];
+          z.op = internOp(bprop, index, typedOp("zero", ad));
+          z.args = {r.args[k]};
+          zeros.push_back(z);
+        }
+      }
+    }
+    for (auto *list : {&zeros, &acc})
+      for (auto &r : *list) {
+        bprop.code.push_back(r.op);
+        for (auto a : r.args) bprop.code.push_back(a);
+        bprop.n_instructions++;
+      }
+  }
+
+  // ---- fprop (gradients.cpp:236-316)
+  {
+    for (auto p : src.inputs) {
+      p.address += G;
+      fprop.inputs.push_back(p);
+    }
+    packOffsets(fprop.inputs);
+    for (auto p : src.outputs) {
+      p.address += G;
+      fprop.outputs.push_back(p);
+    }
+    packOffsets(fprop.outputs);
+    fprop.memory_size = src.memory_size + prep.memory_size;
+    auto index = opIndex(fprop);
+    auto zero = [&](const trxfile::Port &p) {
+      trxfile::ArgDesc ad;
+      ad.size = p.size;
+      ad.lanes = p.lanes;
+      fprop.code.push_back(internOp(fprop, index, typedOp("zero", ad)));
+      fprop.code.push_back(p.address + G);
+      fprop.n_instructions++;
+    };
+    for (auto &p : src.constants) zero(p);
+    for (auto &p : src.parameters) zero(p);
+    for (size_t i = 0; i < insts.size(); i++) {
+      const auto &in = insts[i];
+      std::string fname = variantName(src.ops[in.op].name, "forward");
+      if (!hasOp(fname)) throw std::runtime_error("variant not found: forward " + src.ops[in.op].name);
+      uint32_t id = internOp(fprop, index, fname);
+      fprop.code.push_back(id);
+      size_t n0 = fprop.code.size();
+      if (prep_at[i] < 0) {
+        for (uint32_t k = 0; k < in.n_args; k++) fprop.code.push_back(src.code[in.code_at + k]);
+      } else {
+        for (uint32_t k = in.n_args; k < prep_nargs[i]; k++) fprop.code.push_back(prep.code[prep_at[i] + k]);
+      }
+      for (uint32_t k = 0; k < in.n_args; k++) fprop.code.push_back(src.code[in.code_at + k] + G);
+      if (fprop.code.size() - n0 != fprop.ops[id].args.size())
+        throw std::runtime_error("forward signature mismatch for " + src.ops[in.op].name);
+      fprop.n_instructions++;
+    }
+  }
+
+  // ---- hprop = fprop ; bprop on one memory (gradients.cpp:344-362)
+  {
+    hprop.inputs = fprop.inputs;
+    hprop.outputs = bprop.outputs;
+    auto index = opIndex(hprop);
+    for (auto *part : {&fprop, &bprop}) {
+      for (auto &in : decode(*part)) {
+        hprop.code.push_back(internOp(hprop, index, part->ops[in.op].name));
+        for (uint32_t k = 0; k < in.n_args; k++) hprop.code.push_back(part->code[in.code_at + k]);
+        hprop.n_instructions++;
+      }
+    }
+    hprop.memory_size = std::max(bprop.memory_size, fprop.memory_size);
+  }
+
+  // ---- accu: x (+) delta (gradients.cpp:364-406)
+  {
+    Alloc alloc;
+    std::vector<trxfile::Port> aa, bb, xx;
+    for (auto p : src.inputs) {
+      p.address = alloc.alloc(p.size, p.lanes);
+      aa.push_back(p);
+      accu.inputs.push_back(p);
+    }
+    for (auto p : fprop.inputs) {
+      p.address = alloc.alloc(p.size, p.lanes);
+      bb.push_back(p);
+      accu.inputs.push_back(p);
+    }
+    packOffsets(accu.inputs);
+    for (auto p : src.inputs) {
+      p.address = alloc.alloc(p.size, p.lanes);
+      xx.push_back(p);
+      accu.outputs.push_back(p);
+    }
+    packOffsets(accu.outputs);
+    auto index = opIndex(accu);
+    for (size_t i = 0; i < aa.size(); i++) {
+      trxfile::ArgDesc ad;
+      ad.size = aa[i].size;
+      ad.lanes = aa[i].lanes;
+      uint32_t comps = ad.size / (8 * ad.lanes);
+      // Operator::find<compute, op_add>(aa.type(), bb.type()): scalar add, or the manifold plus for
+      // orientations / poses (add_fg_quat_vec3, add_fg_pose_twist)
+      std::string name = comps == 4 ? std::string("add_fg_quat_vec3") + (ad.lanes == 8 ? "_8d" : "_d")
+                         : comps == 7 ? std::string("add_fg_pose_twist") + (ad.lanes == 8 ? "_8d" : "_d")
+                                      : typedOp("add", ad);
+      accu.code.push_back(internOp(accu, index, name));
+      accu.code.push_back(aa[i].address);
+      accu.code.push_back(bb[i].address);
+      accu.code.push_back(xx[i].address);
+      accu.n_instructions++;
+    }
+    accu.memory_size = alloc.top;
+  }
+}
+
+}  // namespace trxb

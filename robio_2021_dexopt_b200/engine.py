@@ -51,9 +51,12 @@ class Memory:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _native.lib().trx_memory_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _native.lib().trx_memory_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:  # interpreter teardown
+            pass
 
 
 class Executable:
@@ -155,9 +158,12 @@ class Executable:
         return self.outputVector(memory)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _native.lib().trx_program_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _native.lib().trx_program_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:  # interpreter teardown
+            pass
 
 
 class CudaEngine:
