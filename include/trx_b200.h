@@ -167,6 +167,32 @@ uint64_t trx_kernel_launch_count(void);
 /* debug: copy `bytes` of tile `tile`'s memory image starting at byte `address` to the host */
 trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes);
 
+/* ---- objective + gradient (the solver's inner loop) -----------------------------
+ * One call = the engine work of one GradientDescentSolver::_step / the first half of
+ * LeastSquaresSolver::_step (tractor/include/tractor/solvers/gd.h:50-63, solvers/sq.h:69-77):
+ *     x_prog->run(x, mem, r);  loss = r.squaredNorm();  x_prep->execute(mem);  x_bprop->run(r, mem, g);
+ * with r kept on the device.  `lanes` rollouts are evaluated; if their write-once memory images
+ * exceed `max_device_bytes` (0 = no limit) the rollouts are walked in equal chunks and the
+ * gradients summed (rollouts are independent).  The programs must outlive the objective. */
+typedef struct trx_objective trx_objective;
+trx_status trx_objective_create(const trx_program *prog, const trx_program *prep, const trx_program *bprop,
+                                uint64_t lanes, uint64_t max_device_bytes, int device, trx_objective **out);
+void trx_objective_destroy(trx_objective *o);
+/* keys: n_x lanes chunk_lanes n_chunks parameter_bytes device_bytes launches_per_evaluation */
+trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t *value);
+/* per-lane parameters of all rollouts, wide layout, host pointer (Executable::parameterize) */
+trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint64_t bytes, void *stream);
+/* host buffers: x[n_x] in, *loss and gradient[n_x] out; H2D and D2H copies included; synchronous */
+trx_status trx_objective_evaluate(trx_objective *o, const double *x, double *loss, double *gradient, void *stream);
+/* device buffers: d_x[n_x] in, d_out[1 + n_x] = {loss, gradient} out; asynchronous on `stream` */
+trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, double *d_out, void *stream);
+/* CUDA-event times of the last trx_objective_evaluate: {h2d, kernels, d2h} in milliseconds */
+trx_status trx_objective_last_times(const trx_objective *o, float *ms3);
+/* per-program kernel timing with CUDA events on the launching stream: enable, then call
+ * trx_objective_profile_collect after each evaluation; ms3 = running totals {prog, prep+seed, bprop} */
+trx_status trx_objective_set_profiling(trx_objective *o, int enable);
+trx_status trx_objective_profile_collect(trx_objective *o, double *ms3, uint64_t *evaluations);
+
 /* ---- objective assembly (product-side recorder) ------------------------------
  * Stands where dexopt records its problem onto a tape: DexLearn::build ->
  * Program([&]{ _runTraining(); }) (dexopt/src/dexlearn.h:440-453,511-518) followed by

@@ -20,6 +20,7 @@
 // TEST INFRASTRUCTURE ONLY.
 #include <atomic>
 #include <fstream>
+#include <mutex>
 #include <thread>
 
 #include "ref_backend.h"
@@ -264,7 +265,8 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
 
 // Runs K lane tiles through the reference engine and stores the golden arrays.
 static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std::vector<double> &x, size_t n_param_lane,
-                       int tiles, uint64_t seed, const std::string &param_kind) {
+                       int tiles, uint64_t seed, const std::string &param_kind, int gd_steps = 0,
+                       double learning_rate = 0.01) {
   dexsyn::Rng rng(seed);
   RefRunner run(gs);
   size_t nx = portElements(gs.prog.inputs());
@@ -282,6 +284,7 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
   }
   std::vector<double> g_total, h_total;
   double loss_total = 0;
+  std::vector<std::vector<double>> all_params;
   for (int t = 0; t < tiles; t++) {
     std::vector<double> params(n_param_lane * 8);
     for (size_t i = 0; i < params.size(); i++) {
@@ -295,6 +298,7 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
         params[i] = rng.uniform(-0.1, 0.1);
       }
     }
+    all_params.push_back(params);
     std::vector<double> r, v, g, dr, h;
     run.parameterize(params);
     run.forward(x, r);
@@ -331,6 +335,41 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
   bundle.arrays.emplace_back("h_total", h_total);
   bundle.arrays.emplace_back("loss_total", std::vector<double>{loss_total});
   (void)nr;
+
+  // GradientDescentSolver::_step (tractor/include/tractor/solvers/gd.h:43-129) driven a fixed number
+  // of times over all tiles: v <- mu v - lr g (mu = 0, dexopt.cpp:199-202), x <- accumulate(x, v)
+  // through the reference's own accu program (solvers/base.h:158-165).
+  if (gd_steps > 0) {
+    std::vector<double> xk = x, losses, iterates;
+    for (int step = 0; step < gd_steps; step++) {
+      std::vector<double> g_sum(nx, 0.0);
+      double loss = 0;
+      for (int t = 0; t < tiles; t++) {
+        std::vector<double> r, g;
+        run.parameterize(all_params[t]);
+        run.forward(xk, r);
+        run.prepare();
+        for (size_t i = 0; i < r.size(); i++) {
+          if (t > 0 && scalar_out[i]) r[i] = 0;
+          loss += r[i] * r[i];
+        }
+        run.reverse(r, g);
+        for (size_t i = 0; i < nx; i++) g_sum[i] += g[i];
+      }
+      std::vector<double> ab(2 * nx), xn;
+      for (size_t i = 0; i < nx; i++) {
+        ab[i] = xk[i];
+        ab[nx + i] = -learning_rate * g_sum[i];
+      }
+      run.x_accu->run(ab, run.memory, xn);
+      xk = xn;
+      losses.push_back(loss);
+      iterates.insert(iterates.end(), xk.begin(), xk.end());
+    }
+    bundle.arrays.emplace_back("gd/loss", losses);
+    bundle.arrays.emplace_back("gd/x", iterates);
+    bundle.arrays.emplace_back("gd/learning_rate", std::vector<double>{learning_rate});
+  }
 }
 
 static int cmdRecord(const std::string &path, const std::map<std::string, std::string> &kv) {
@@ -362,7 +401,9 @@ static int cmdRecord(const std::string &path, const std::map<std::string, std::s
   }
   bundle.texts.emplace_back("meta", meta);
   gs.addTo(bundle);
-  if (tiles > 0) goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem);
+  if (tiles > 0)
+    goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem,
+               (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01));
   else bundle.arrays.emplace_back("x", x);
   trxfile::writeBundle(bundle, path);
   std::cerr << meta;
@@ -387,7 +428,14 @@ static int cmdBench(const std::map<std::string, std::string> &kv) {
   auto t0 = std::chrono::steady_clock::now();
   for (int ti = 0; ti < threads; ti++) {
     pool.emplace_back([&, ti]() {
-      RefRunner run(gs, loop);  // own Memory + executables per thread
+      std::unique_ptr<RefRunner> runp;
+      {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        MuteCout mute;  // LoopEngine prints its schedule while compiling
+        runp.reset(new RefRunner(gs, loop));  // own Memory + executables per thread
+      }
+      RefRunner &run = *runp;
       dexsyn::Rng rng(1000 + ti);
       std::vector<double> params(n_param_lane * 8), r, g;
       while (!stop.load()) {

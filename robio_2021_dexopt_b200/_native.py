@@ -53,6 +53,17 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
     L.trx_execute.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     L.trx_memory_peek.argtypes = [c.c_void_p, c.c_uint64, c.c_uint64, c.c_void_p, c.c_uint64]
+    L.trx_objective_create.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_uint64, c.c_int,
+                                       c.POINTER(c.c_void_p)]
+    L.trx_objective_destroy.argtypes = [c.c_void_p]
+    L.trx_objective_destroy.restype = None
+    L.trx_objective_info.argtypes = [c.c_void_p, c.c_char_p, c.POINTER(c.c_uint64)]
+    L.trx_objective_parameterize.argtypes = [c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
+    L.trx_objective_evaluate.argtypes = [c.c_void_p, c.c_void_p, c.POINTER(c.c_double), c.c_void_p, c.c_void_p]
+    L.trx_objective_evaluate_device.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    L.trx_objective_last_times.argtypes = [c.c_void_p, c.POINTER(c.c_float)]
+    L.trx_objective_set_profiling.argtypes = [c.c_void_p, c.c_int]
+    L.trx_objective_profile_collect.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]
     L.trx_dexsyn_build.argtypes = [c.c_char_p, c.POINTER(c.POINTER(c.c_uint8)), c.POINTER(c.c_uint64)]
     L.trx_builder_free.argtypes = [c.POINTER(c.c_uint8)]
     L.trx_builder_free.restype = None

@@ -20,7 +20,7 @@ extern "C" {
 const char *trx_builder_last_error(void) { return g_builder_error.c_str(); }
 
 // options: "key=value" pairs separated by spaces; keys: kind frames outer hidden dropout seed
-//          joints contacts extra_fixed wstd
+//          joints contacts extra_fixed wstd programs (comma separated subset of prog,prep,fprop,bprop,hprop,accu)
 // On success *out points to a malloc'ed TRXB bundle (free with trx_builder_free) containing programs
 // prog/prep/fprop/bprop/hprop/accu, array "x" (initial policy parameters) and text "meta".
 int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
@@ -85,12 +85,16 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     meta += "n_joints=" + std::to_string(model.joints.size()) + "\n";
     meta += "n_end_effectors=" + std::to_string(model.end_effectors.size()) + "\n";
     bundle.texts.emplace_back("meta", meta);
-    bundle.programs.emplace_back("prog", std::move(b.prog));
-    bundle.programs.emplace_back("prep", std::move(g.prep));
-    bundle.programs.emplace_back("fprop", std::move(g.fprop));
-    bundle.programs.emplace_back("bprop", std::move(g.bprop));
-    bundle.programs.emplace_back("hprop", std::move(g.hprop));
-    bundle.programs.emplace_back("accu", std::move(g.accu));
+    std::string want = "," + getS("programs", "prog,prep,fprop,bprop,hprop,accu") + ",";
+    auto put = [&](const char *name, trxfile::Program &p) {
+      if (want.find(std::string(",") + name + ",") != std::string::npos) bundle.programs.emplace_back(name, std::move(p));
+    };
+    put("prog", b.prog);
+    put("prep", g.prep);
+    put("fprop", g.fprop);
+    put("bprop", g.bprop);
+    put("hprop", g.hprop);
+    put("accu", g.accu);
     bundle.arrays.emplace_back("x", x0);
     std::vector<uint8_t> bytes;
     trxfile::encodeBundle(bundle, bytes);

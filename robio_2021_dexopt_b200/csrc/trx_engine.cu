@@ -105,8 +105,11 @@ struct DevElem {
 
 // wide packed buffer -> tile images (base.cpp:9-31).  scalar_once: scalar-typed values go to tile 0
 // only and the other tiles get zero (reverse-mode programs).
+// `lanes` is the lane count of the wide buffer, `lane_base` the first lane handled by tile 0 of this
+// memory (non-zero when an objective walks its rollouts in chunks).
 __global__ void trx_scatter_kernel(const DevElem *__restrict__ elems, uint32_t n, const double *__restrict__ wide,
-                                   uint64_t lanes, double *mem, uint64_t tile_stride, int scalar_once) {
+                                   uint64_t lanes, uint64_t lane_base, double *mem, uint64_t tile_stride,
+                                   int scalar_once) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t tile = blockIdx.y;
@@ -114,18 +117,19 @@ __global__ void trx_scatter_kernel(const DevElem *__restrict__ elems, uint32_t n
   double v;
   if (e.lane == 0xff) {
     v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes];
-    if (scalar_once && tile != 0) v = 0.0;
+    if (scalar_once && (tile != 0 || lane_base != 0)) v = 0.0;
   } else {
-    v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + tile * 8 + e.lane];
+    v = wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + lane_base + tile * 8 + e.lane];
   }
   mem[tile * tile_stride + e.idx] = v;
 }
 
 // tile images -> wide packed buffer (base.cpp:33-40).  scalar_sum: scalar-typed values are summed
 // over the tiles in tile order (deterministic); otherwise they are read from tile 0.
+// accumulate: scalar-typed sums are added to what `wide` already holds (chunked objectives).
 __global__ void trx_gather_kernel(const DevElem *__restrict__ elems, uint32_t n, double *__restrict__ wide,
-                                  uint64_t lanes, const double *mem, uint64_t tile_stride, uint32_t n_tiles,
-                                  int scalar_sum) {
+                                  uint64_t lanes, uint64_t lane_base, const double *mem, uint64_t tile_stride,
+                                  uint32_t n_tiles, int scalar_sum, int accumulate) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t tile = blockIdx.y;
@@ -135,10 +139,55 @@ __global__ void trx_gather_kernel(const DevElem *__restrict__ elems, uint32_t n,
     double v = mem[e.idx];
     if (scalar_sum)
       for (uint32_t t = 1; t < n_tiles; t++) v += mem[(uint64_t)t * tile_stride + e.idx];
-    wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes] = v;
+    double *dst = wide + (uint64_t)e.fixed + (uint64_t)e.per_lane * lanes;
+    *dst = accumulate ? (*dst + v) : v;
   } else {
-    wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + tile * 8 + e.lane] = mem[tile * tile_stride + e.idx];
+    wide[(uint64_t)e.fixed + (uint64_t)e.per_lane * lanes + lane_base + tile * 8 + e.lane] =
+        mem[tile * tile_stride + e.idx];
   }
+}
+
+// Objective glue (solvers/gd.h:50-63): r = outputs of the forward tape stay in the tile image;
+// this kernel seeds the adjoint sweep with them (gradient slot = forward slot + prep.memory_size,
+// gradients.cpp:80-86) and accumulates loss = |r|^2 per tile.  Scalar-typed residual rows are
+// identical in every tile and count once.
+struct SeedElem {
+  uint32_t src, dst;
+  uint32_t scalar;
+};
+__global__ void trx_seed_kernel(const SeedElem *__restrict__ elems, uint32_t n, double *mem, uint64_t tile_stride,
+                                int first_chunk, double *__restrict__ partial) {
+  __shared__ double red[256];
+  double *m = mem + (uint64_t)blockIdx.x * tile_stride;
+  bool owner = first_chunk && blockIdx.x == 0;
+  double acc = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    SeedElem e = elems[i];
+    double v = m[e.src];
+    if (e.scalar && !owner) v = 0.0;
+    m[e.dst] = v;
+    acc += v * v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+// fixed-order sum of the per-tile partials: out[0] (+)= sum
+__global__ void trx_loss_kernel(const double *__restrict__ partial, uint32_t n, double *out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
 }
 
 }  // namespace
@@ -216,9 +265,10 @@ template <class T> trx_status upload(const std::vector<T> &v, T **dst) {
 }
 
 trx_status scatterDevice(const trx_program *p, trx_memory *m, int which, const double *d_wide, uint64_t bytes,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, uint64_t wide_lanes = 0, uint64_t lane_base = 0) {
   const trx::PortLayout &L = p->layout(which);
-  uint64_t expect = L.wideElems(m->lanes) * 8;
+  if (wide_lanes == 0) wide_lanes = m->lanes;
+  uint64_t expect = L.wideElems(wide_lanes) * 8;
   if (bytes != expect)
     return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
                                   std::to_string(expect));
@@ -228,7 +278,8 @@ trx_status scatterDevice(const trx_program *p, trx_memory *m, int which, const d
   if (n == 0) return TRX_OK;
   dim3 grid((n + 255) / 256, (unsigned)m->n_tiles);
   int once = (which == TRX_BUF_INPUT && p->scalar_inputs == TRX_SCALAR_REDUCE) ? 1 : 0;
-  trx_scatter_kernel<<<grid, 256, 0, stream>>>(p->d_elems[which], n, d_wide, m->lanes, m->d_mem, m->tile_stride, once);
+  trx_scatter_kernel<<<grid, 256, 0, stream>>>(p->d_elems[which], n, d_wide, wide_lanes, lane_base, m->d_mem,
+                                               m->tile_stride, once);
   g_launches++;
   TRX_CUDA(cudaGetLastError());
   return TRX_OK;
@@ -469,15 +520,8 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
   }
   if (p->low.n_instructions) {
     uint32_t W = p->low.n_warps;
-    if (W <= 8)
-      trx_vm_kernel<8><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                 m->tile_stride);
-    else if (W <= 16)
-      trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                  m->tile_stride);
-    else
-      trx_vm_kernel<32><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                  m->tile_stride);
+    trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                m->tile_stride);
     g_launches++;
   }
   TRX_CUDA(cudaGetLastError());
@@ -498,9 +542,9 @@ trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed
   uint32_t n = p->n_elems[TRX_BUF_OUTPUT];
   if (n == 0) return TRX_OK;
   dim3 grid((n + 255) / 256, (unsigned)m->n_tiles);
-  trx_gather_kernel<<<grid, 256, 0, stream>>>(p->d_elems[TRX_BUF_OUTPUT], n, (double *)d_packed, m->lanes, m->d_mem,
+  trx_gather_kernel<<<grid, 256, 0, stream>>>(p->d_elems[TRX_BUF_OUTPUT], n, (double *)d_packed, m->lanes, 0, m->d_mem,
                                              m->tile_stride, (uint32_t)m->n_tiles,
-                                             p->scalar_outputs == TRX_SCALAR_REDUCE ? 1 : 0);
+                                             p->scalar_outputs == TRX_SCALAR_REDUCE ? 1 : 0, 0);
   g_launches++;
   TRX_CUDA(cudaGetLastError());
   return TRX_OK;
@@ -532,6 +576,247 @@ trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void 
   TRX_CUDA(cudaDeviceSynchronize());
   TRX_CUDA(cudaMemcpy(dst, (const uint8_t *)m->d_mem + tile * m->tile_stride * 8 + address, bytes,
                       cudaMemcpyDeviceToHost));
+  return TRX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ objective (solver-level glue)
+
+struct trx_objective {
+  const trx_program *prog = nullptr, *prep = nullptr, *bprop = nullptr;
+  int device = 0;
+  uint64_t lanes = 0, chunk_lanes = 0, n_chunks = 0;
+  uint64_t n_x = 0;
+  trx_memory *mem = nullptr;
+  double *d_x = nullptr, *d_params = nullptr, *d_out = nullptr, *d_partial = nullptr;
+  double *h_x = nullptr, *h_out = nullptr;  // pinned
+  uint64_t param_elems = 0;
+  SeedElem *d_seed = nullptr;
+  uint32_t n_seed = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[3] = {0, 0, 0};
+  // optional per-program kernel timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // 4 per chunk: before prog, after prog, after prep(+seed), after bprop
+  double prof_ms[3] = {0, 0, 0};
+  uint64_t prof_count = 0;
+};
+
+extern "C" {
+
+trx_status trx_objective_create(const trx_program *prog, const trx_program *prep, const trx_program *bprop,
+                                uint64_t lanes, uint64_t max_device_bytes, int device, trx_objective **out) {
+  if (!prog || !prep || !bprop || !out) return fail(TRX_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
+  const auto &po = prog->low.outputs.elems;
+  const auto &bi = bprop->low.inputs.elems;
+  if (po.size() != bi.size()) return fail(TRX_ERR_INVALID, "bprop inputs do not mirror prog outputs");
+  for (auto &e : prog->low.inputs.elems)
+    if (e.lane != 0xff) return fail(TRX_ERR_UNSUPPORTED, "objective: lane-typed optimisation variables are not supported");
+  if (bprop->low.outputs.elems.size() != prog->low.inputs.elems.size())
+    return fail(TRX_ERR_INVALID, "bprop outputs do not mirror prog inputs");
+  TRX_CUDA(cudaSetDevice(device));
+  std::unique_ptr<trx_objective> o(new trx_objective());
+  o->prog = prog;
+  o->prep = prep;
+  o->bprop = bprop;
+  o->device = device;
+  o->lanes = lanes;
+  o->n_x = prog->low.inputs.elems.size();
+  // lane chunking: rollouts are independent, so when the write-once memory image of all tiles does
+  // not fit the budget the tiles are evaluated in equal chunks and the gradients summed
+  uint64_t per_tile = std::max(std::max(prog->low.memory_size, prep->low.memory_size), bprop->low.memory_size);
+  uint64_t tiles = lanes / 8;
+  uint64_t budget_tiles = max_device_bytes ? std::max<uint64_t>(1, max_device_bytes / per_tile) : tiles;
+  uint64_t chunk_tiles = std::min(tiles, budget_tiles);
+  while (tiles % chunk_tiles) chunk_tiles--;
+  o->chunk_lanes = chunk_tiles * 8;
+  o->n_chunks = tiles / chunk_tiles;
+  trx_status s = trx_memory_create(o->chunk_lanes, device, &o->mem);
+  if (s != TRX_OK) return s;
+  s = ensureTileStride(o->mem, per_tile, 0);
+  if (s != TRX_OK) return s;
+  std::vector<SeedElem> seed(po.size());
+  for (size_t i = 0; i < po.size(); i++) {
+    if (po[i].lane != bi[i].lane) return fail(TRX_ERR_INVALID, "bprop inputs do not mirror prog outputs");
+    seed[i] = {po[i].idx, bi[i].idx, po[i].lane == 0xff ? 1u : 0u};
+  }
+  o->n_seed = (uint32_t)seed.size();
+  if ((s = upload(seed, &o->d_seed)) != TRX_OK) return s;
+  o->param_elems = prog->low.parameters.wideElems(lanes);
+  TRX_CUDA(cudaMalloc(&o->d_x, std::max<uint64_t>(1, o->n_x) * 8));
+  TRX_CUDA(cudaMalloc(&o->d_params, std::max<uint64_t>(1, o->param_elems) * 8));
+  TRX_CUDA(cudaMemset(o->d_params, 0, std::max<uint64_t>(1, o->param_elems) * 8));
+  TRX_CUDA(cudaMalloc(&o->d_out, (o->n_x + 1) * 8));
+  TRX_CUDA(cudaMalloc(&o->d_partial, tiles * 8));
+  TRX_CUDA(cudaMallocHost(&o->h_x, std::max<uint64_t>(1, o->n_x) * 8));
+  TRX_CUDA(cudaMallocHost(&o->h_out, (o->n_x + 1) * 8));
+  for (auto &e : o->ev) TRX_CUDA(cudaEventCreate(&e));
+  *out = o.release();
+  return TRX_OK;
+}
+
+void trx_objective_destroy(trx_objective *o) {
+  if (!o) return;
+  trx_memory_destroy(o->mem);
+  cudaFree(o->d_x);
+  cudaFree(o->d_params);
+  cudaFree(o->d_out);
+  cudaFree(o->d_partial);
+  cudaFree(o->d_seed);
+  if (o->h_x) cudaFreeHost(o->h_x);
+  if (o->h_out) cudaFreeHost(o->h_out);
+  for (auto &e : o->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto &e : o->prof_events) cudaEventDestroy(e);
+  delete o;
+}
+
+trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t *value) {
+  if (!o || !key || !value) return fail(TRX_ERR_INVALID, "bad argument");
+  std::string k = key;
+  if (k == "n_x") *value = o->n_x;
+  else if (k == "lanes") *value = o->lanes;
+  else if (k == "chunk_lanes") *value = o->chunk_lanes;
+  else if (k == "n_chunks") *value = o->n_chunks;
+  else if (k == "parameter_bytes") *value = o->param_elems * 8;
+  else if (k == "device_bytes") *value = o->mem->tile_stride * o->mem->n_tiles * 8;
+  else if (k == "launches_per_evaluation") {
+    uint64_t per_chunk = 0;
+    per_chunk += o->param_elems ? 1 : 0;                       // parameter scatter
+    per_chunk += 1;                                            // input scatter
+    per_chunk += (o->prog->low.const_idx.empty() ? 0 : 1) + 1; // prog
+    per_chunk += 1;                                            // seed
+    per_chunk += (o->prep->low.n_instructions ? 1 : 0);        // prep
+    per_chunk += (o->bprop->low.n_instructions ? 1 : 0);       // bprop
+    per_chunk += 1;                                            // gradient gather
+    *value = per_chunk * o->n_chunks + 1;
+  } else return fail(TRX_ERR_INVALID, "unknown key " + k);
+  return TRX_OK;
+}
+
+// per-lane parameters of all `lanes` rollouts (wide layout), host pointer
+trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint64_t bytes, void *stream_) {
+  if (!o || (!packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  if (bytes != o->param_elems * 8)
+    return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+                                  std::to_string(o->param_elems * 8));
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (bytes) {
+    TRX_CUDA(cudaMemcpyAsync(o->d_params, packed, bytes, cudaMemcpyHostToDevice, stream));
+    TRX_CUDA(cudaStreamSynchronize(stream));
+  }
+  return TRX_OK;
+}
+
+// The hot path.  x on the device (n_x doubles) -> d_out = [loss, g_0 .. g_{n_x-1}] on the device.
+// Sequence per chunk = GradientDescentSolver::_step's engine calls (solvers/gd.h:50-63):
+// x_prog input+execute, loss = |r|^2, x_prep execute, x_bprop input(r)+execute+output.
+trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, double *d_out, void *stream_) {
+  if (!o || !d_x || !d_out) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  trx_memory *m = o->mem;
+  const uint64_t chunk_tiles = m->n_tiles;
+  for (uint64_t c = 0; c < o->n_chunks; c++) {
+    trx_status s;
+    if (o->param_elems) {
+      s = scatterDevice(o->prog, m, TRX_BUF_PARAMETER, o->d_params, o->param_elems * 8, stream, o->lanes,
+                        c * o->chunk_lanes);
+      if (s != TRX_OK) return s;
+    }
+    s = scatterDevice(o->prog, m, TRX_BUF_INPUT, d_x, o->n_x * 8, stream, o->lanes, c * o->chunk_lanes);
+    if (s != TRX_OK) return s;
+    cudaEvent_t *pe = o->profiling ? &o->prof_events[c * 4] : nullptr;
+    if (pe) cudaEventRecord(pe[0], stream);
+    if ((s = trx_execute(o->prog, m, stream_)) != TRX_OK) return s;
+    if (pe) cudaEventRecord(pe[1], stream);
+    trx_seed_kernel<<<(unsigned)chunk_tiles, 256, 0, stream>>>(o->d_seed, o->n_seed, m->d_mem, m->tile_stride,
+                                                              c == 0 ? 1 : 0, o->d_partial + c * chunk_tiles);
+    g_launches++;
+    if ((s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
+    if (pe) cudaEventRecord(pe[2], stream);
+    if ((s = trx_execute(o->bprop, m, stream_)) != TRX_OK) return s;
+    if (pe) cudaEventRecord(pe[3], stream);
+    uint32_t n = o->bprop->n_elems[TRX_BUF_OUTPUT];
+    dim3 grid((n + 255) / 256, 1);
+    trx_gather_kernel<<<grid, 256, 0, stream>>>(o->bprop->d_elems[TRX_BUF_OUTPUT], n, d_out + 1, o->lanes, 0, m->d_mem,
+                                               m->tile_stride, (uint32_t)chunk_tiles, 1, c == 0 ? 0 : 1);
+    g_launches++;
+  }
+  trx_loss_kernel<<<1, 256, 0, stream>>>(o->d_partial, (uint32_t)(o->lanes / 8), d_out);
+  g_launches++;
+  TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+// Host-buffer variant (the reference-facing call): copies x from `x` (n_x doubles) through pinned
+// memory, evaluates, and returns loss and gradient (n_x doubles) to the host; synchronous.
+trx_status trx_objective_evaluate(trx_objective *o, const double *x, double *loss, double *gradient, void *stream_) {
+  if (!o || !x || !loss || !gradient) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::memcpy(o->h_x, x, o->n_x * 8);
+  TRX_CUDA(cudaEventRecord(o->ev[0], stream));
+  TRX_CUDA(cudaMemcpyAsync(o->d_x, o->h_x, o->n_x * 8, cudaMemcpyHostToDevice, stream));
+  TRX_CUDA(cudaEventRecord(o->ev[1], stream));
+  trx_status s = trx_objective_evaluate_device(o, o->d_x, o->d_out, stream_);
+  if (s != TRX_OK) return s;
+  TRX_CUDA(cudaEventRecord(o->ev[2], stream));
+  TRX_CUDA(cudaMemcpyAsync(o->h_out, o->d_out, (o->n_x + 1) * 8, cudaMemcpyDeviceToHost, stream));
+  TRX_CUDA(cudaEventRecord(o->ev[3], stream));
+  TRX_CUDA(cudaStreamSynchronize(stream));
+  *loss = o->h_out[0];
+  std::memcpy(gradient, o->h_out + 1, o->n_x * 8);
+  cudaEventElapsedTime(&o->last_ms[0], o->ev[0], o->ev[1]);
+  cudaEventElapsedTime(&o->last_ms[1], o->ev[1], o->ev[2]);
+  cudaEventElapsedTime(&o->last_ms[2], o->ev[2], o->ev[3]);
+  return TRX_OK;
+}
+
+// Per-program kernel timing.  enable: CUDA events are recorded around the prog / prep(+seed) / bprop
+// launches of every chunk; trx_objective_profile_collect (after a stream synchronise) adds the
+// elapsed times of the last evaluation to running totals {prog, prep, bprop} in milliseconds.
+trx_status trx_objective_set_profiling(trx_objective *o, int enable) {
+  if (!o) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(o->device));
+  o->profiling = enable != 0;
+  if (o->profiling && o->prof_events.empty()) {
+    o->prof_events.resize(o->n_chunks * 4);
+    for (auto &e : o->prof_events) TRX_CUDA(cudaEventCreate(&e));
+  }
+  o->prof_ms[0] = o->prof_ms[1] = o->prof_ms[2] = 0;
+  o->prof_count = 0;
+  return TRX_OK;
+}
+trx_status trx_objective_profile_collect(trx_objective *o, double *ms3, uint64_t *evaluations) {
+  if (!o || !ms3) return fail(TRX_ERR_INVALID, "bad argument");
+  if (!o->profiling) return fail(TRX_ERR_INVALID, "profiling is not enabled");
+  TRX_CUDA(cudaSetDevice(o->device));
+  for (uint64_t c = 0; c < o->n_chunks; c++) {
+    cudaEvent_t *pe = &o->prof_events[c * 4];
+    TRX_CUDA(cudaEventSynchronize(pe[3]));
+    for (int k = 0; k < 3; k++) {
+      float ms = 0;
+      TRX_CUDA(cudaEventElapsedTime(&ms, pe[k], pe[k + 1]));
+      o->prof_ms[k] += ms;
+    }
+  }
+  o->prof_count++;
+  for (int k = 0; k < 3; k++) ms3[k] = o->prof_ms[k];
+  if (evaluations) *evaluations = o->prof_count;
+  return TRX_OK;
+}
+
+// device times of the last trx_objective_evaluate call: h2d, kernels, d2h (milliseconds, CUDA events)
+trx_status trx_objective_last_times(const trx_objective *o, float *ms3) {
+  if (!o || !ms3) return fail(TRX_ERR_INVALID, "bad argument");
+  ms3[0] = o->last_ms[0];
+  ms3[1] = o->last_ms[1];
+  ms3[2] = o->last_ms[2];
   return TRX_OK;
 }
 

@@ -76,7 +76,7 @@ inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32
 }
 
 struct LowerOptions {
-  uint32_t n_warps = 8;
+  uint32_t n_warps = 16;
 };
 
 struct LoweredProgram {
@@ -99,7 +99,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   out = LoweredProgram();
   out.memory_size = (src.memory_size + 255) / 256 * 256;
   out.n_warps = opt.n_warps;
-  if (opt.n_warps < 1 || opt.n_warps > 32) throw std::runtime_error("n_warps out of range");
+  if (opt.n_warps < 1 || opt.n_warps > 16) throw std::runtime_error("n_warps out of range (1..16)");
   if (src.memory_size / 8 >= 0xffffffffull) throw std::runtime_error("memory image too large for 32-bit slot indices");
 
   // ---- 1. operator table -> opcodes, signature check

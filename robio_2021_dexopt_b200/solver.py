@@ -1,0 +1,111 @@
+"""Host mirror of the optimiser loop that calls the hot path.
+
+Reference being mirrored:
+    tractor/include/tractor/solvers/base.h:112-182   SolverBase: compiles prog/prep/bprop/... on one Memory
+    tractor/include/tractor/solvers/gd.h:43-129      GradientDescentSolver::_step
+    tractor/src/core/solver.cpp:52-103               Solver::gather / solve / scatter / step / loss
+The engine work of one step (x_prog, loss, x_prep, x_bprop) is a single C-ABI call,
+trx_objective_evaluate (include/trx_b200.h); the update rule runs on the host on the
+8 083-element parameter vector exactly as gd.h:74,96 write it:  v <- mu v - lr g ;  x <- x (+) v.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _native, trxfile
+from ._native import check
+from .engine import CudaEngine
+
+
+class Objective:
+    """objective + gradient over R rollouts of a recorded problem (prog/prep/bprop of one bundle)"""
+
+    def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0):
+        self.engine = engine
+        self.x_prog = engine.compile(bundle.programs["prog"])
+        self.x_prep = engine.compile(bundle.programs["prep"])
+        self.x_bprop = engine.compile(bundle.programs["bprop"])
+        self._h = ctypes.c_void_p()
+        check(_native.lib().trx_objective_create(self.x_prog._h, self.x_prep._h, self.x_bprop._h, lanes,
+                                                 max_device_bytes, engine.device, ctypes.byref(self._h)))
+        self.lanes = lanes
+        self.n_x = self.info("n_x")
+        self._g = np.empty(self.n_x)
+
+    def info(self, key: str) -> int:
+        v = ctypes.c_uint64()
+        check(_native.lib().trx_objective_info(self._h, key.encode(), ctypes.byref(v)))
+        return v.value
+
+    def parameterize(self, wide_params: np.ndarray) -> None:
+        b = np.ascontiguousarray(wide_params, dtype=np.float64)
+        check(_native.lib().trx_objective_parameterize(self._h, b.ctypes.data, b.nbytes, None))
+
+    def evaluate(self, x: np.ndarray):
+        """host x -> (loss, gradient); H2D of x and D2H of (loss, g) happen inside"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.n_x
+        loss = ctypes.c_double()
+        check(_native.lib().trx_objective_evaluate(self._h, x.ctypes.data, ctypes.byref(loss), self._g.ctypes.data,
+                                                   None))
+        return loss.value, self._g.copy()
+
+    def evaluate_device(self, d_x_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
+        check(_native.lib().trx_objective_evaluate_device(self._h, ctypes.c_void_p(d_x_ptr),
+                                                          ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
+
+    def set_profiling(self, enable: bool) -> None:
+        check(_native.lib().trx_objective_set_profiling(self._h, 1 if enable else 0))
+
+    def profile_collect(self):
+        """running totals of CUDA-event kernel time {prog, prep+seed, bprop} in ms, and evaluation count"""
+        ms = (ctypes.c_double * 3)()
+        n = ctypes.c_uint64()
+        check(_native.lib().trx_objective_profile_collect(self._h, ms, ctypes.byref(n)))
+        return [float(ms[0]), float(ms[1]), float(ms[2])], n.value
+
+    def last_times_ms(self):
+        ms = (ctypes.c_float * 3)()
+        check(_native.lib().trx_objective_last_times(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _native.lib().trx_objective_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class GradientDescentSolver:
+    """GradientDescentSolver (solvers/gd.h:14-129): momentum gradient descent on J^T r."""
+
+    def __init__(self, objective: Objective, learning_rate: float = 0.01, momentum: float = 0.0):
+        self.objective = objective
+        self.learning_rate = learning_rate  # dexopt.cpp:199-202 uses 0.01 / 0
+        self.momentum = momentum
+        self.x: Optional[np.ndarray] = None
+        self.v: Optional[np.ndarray] = None
+        self._loss = float("nan")
+
+    def gather(self, x0: np.ndarray) -> None:  # solver.cpp:52-60
+        self.x = np.array(x0, dtype=np.float64)
+        self.v = np.zeros_like(self.x)
+
+    def step(self) -> float:  # gd.h:43-129
+        loss, g = self.objective.evaluate(self.x)
+        self._loss = loss
+        if np.all(np.isfinite(g)):  # gd.h:72,124-126: non-finite gradients skip the update
+            self.v = self.momentum * self.v - self.learning_rate * g
+            self.x = self.x + self.v  # accu program for scalar inputs: plain add (gradients.cpp:396-403)
+        return loss
+
+    def loss(self) -> float:  # gd.h:40-41
+        return self._loss
+
+    def scatter(self) -> np.ndarray:  # solver.cpp:62-66
+        return self.x.copy()

@@ -11,9 +11,9 @@ G=tests/golden
 $R registry $G/ref_registry.txt
 $R optests $G/optests_8d.trxb suffix=8d seed=7
 $R optests $G/optests_d.trxb suffix=d seed=7
-$R record $G/fkchain24.trxb problem=fkchain joints=24 tiles=2
-$R record /tmp/dexsyn_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4
-$R record /tmp/dexsyn_dropout_outer2.trxb problem=dexsyn frames=2 hidden=4 tiles=2 extra_fixed=2 dropout=1 outer=2
+$R record $G/fkchain24.trxb problem=fkchain joints=24 tiles=2 gd_steps=10
+$R record /tmp/dexsyn_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 gd_steps=10
+$R record /tmp/dexsyn_dropout_outer2.trxb problem=dexsyn frames=2 hidden=4 tiles=2 extra_fixed=2 dropout=1 outer=2 gd_steps=10
 xz -9 -f -c /tmp/dexsyn_small.trxb > $G/dexsyn_small.trxb.xz
 xz -9 -f -c /tmp/dexsyn_dropout_outer2.trxb > $G/dexsyn_dropout_outer2.trxb.xz
 ls -la $G

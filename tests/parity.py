@@ -98,3 +98,36 @@ def check_problem(engine, bundle, n_tiles=None, check_tangent=True):
         dr_want = trxfile.tiles_to_wide(fprop.outputs, tile_arrays(bundle, "dr")[:n_tiles])
         assert_close(dr, dr_want, "tangent")
     return r, g
+
+
+def check_gd_iterates(make_step, bundle, steps=10):
+    """first `steps` GradientDescentSolver iterates against the reference's (solvers/gd.h:43-129,
+    lr 0.01, momentum 0 as dexopt.cpp:199-202); tolerance 1e-9 relative as the north star asks"""
+    nx = bundle.arrays["x"].size
+    want_x = bundle.arrays["gd/x"].reshape(-1, nx)
+    want_loss = bundle.arrays["gd/loss"]
+    assert want_x.shape[0] >= steps
+    for k in range(steps):
+        loss, x = make_step()
+        assert abs(loss - want_loss[k]) <= 1e-9 * abs(want_loss[k]), "GD step %d loss %.17g vs %.17g" % (k, loss, want_loss[k])
+        assert_close(x, want_x[k], "GD iterate %d" % (k + 1), rtol=1e-9, atol=1e-12)
+
+
+class ExecutableObjective:
+    """objective + gradient written against the Executable interface only (works on any engine)"""
+
+    def __init__(self, engine, bundle, n_tiles):
+        self.prog = bundle.view("prog")
+        self.x_prog = engine.compile(bundle.programs["prog"])
+        self.x_prep = engine.compile(bundle.programs["prep"])
+        self.x_bprop = engine.compile(bundle.programs["bprop"])
+        self.mem = engine.createMemory(8 * n_tiles)
+        params = tile_arrays(bundle, "params")[:n_tiles]
+        if self.prog.parameters:
+            self.x_prog.parameterize(trxfile.tiles_to_wide(self.prog.parameters, params), self.mem)
+
+    def evaluate(self, x):
+        r = self.x_prog.run(x, self.mem)
+        self.x_prep.execute(self.mem)
+        g = self.x_bprop.run(r, self.mem)
+        return float(np.dot(r, r)), g

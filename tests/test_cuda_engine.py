@@ -131,3 +131,55 @@ def test_many_tiles_replicate_the_reference_tile(cuda_engine, golden):
         off += n
     g_lane = x_bprop.run(r1_lane, mem1)
     parity.assert_close(g, g_lane * tiles + (g_full - g_lane), "gradient over %d tiles" % tiles, rtol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
+@pytest.mark.parametrize("max_bytes", [0, 1])
+def test_objective_matches_reference(cuda_engine, golden, fixture, max_bytes):
+    """trx_objective_evaluate (one C-ABI call per solver step) against the reference's loss and J^T r;
+    max_bytes=1 forces one lane tile per chunk, i.e. the chunked walk over rollouts"""
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    bundle = golden(fixture)
+    prog = bundle.view("prog")
+    obj = pkg.Objective(cuda_engine, bundle, lanes=16, max_device_bytes=max_bytes)
+    assert obj.info("n_chunks") == (2 if max_bytes else 1)
+    obj.parameterize(trxfile.tiles_to_wide(prog.parameters, parity.tile_arrays(bundle, "params")))
+    loss, g = obj.evaluate(bundle.arrays["x"])
+    want = float(bundle.arrays["loss_total"][0])
+    assert abs(loss - want) <= 1e-11 * abs(want)
+    parity.assert_close(g, bundle.arrays["g_total"], "gradient")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
+def test_gradient_descent_iterates_match_reference(cuda_engine, golden, fixture):
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    bundle = golden(fixture)
+    obj = pkg.Objective(cuda_engine, bundle, lanes=16)
+    obj.parameterize(trxfile.tiles_to_wide(bundle.view("prog").parameters, parity.tile_arrays(bundle, "params")))
+    solver = pkg.GradientDescentSolver(obj, learning_rate=float(bundle.arrays["gd/learning_rate"][0]), momentum=0.0)
+    solver.gather(bundle.arrays["x"])
+
+    def step():
+        loss = solver.step()
+        return loss, solver.scatter()
+
+    parity.check_gd_iterates(step, bundle)
+
+
+@pytest.mark.gpu
+def test_product_built_problem_on_gpu(cuda_engine, golden):
+    """the product's own recorder + gradients + CUDA engine, end to end, against reference numbers"""
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("dexsyn_small.trxb.xz")
+    mine = pkg.build_dexsyn(frames=3, hidden=4, extra_fixed=4)
+    obj = pkg.Objective(cuda_engine, mine, lanes=16)
+    obj.parameterize(trxfile.tiles_to_wide(mine.view("prog").parameters, parity.tile_arrays(ref, "params")))
+    loss, g = obj.evaluate(ref.arrays["x"])
+    want = float(ref.arrays["loss_total"][0])
+    assert abs(loss - want) <= 1e-11 * abs(want)
+    parity.assert_close(g, ref.arrays["g_total"], "gradient")

@@ -33,3 +33,19 @@ def test_level_schedule_is_shallower_than_the_tape(emu_engine, golden):
     assert x.stat("n_levels") < x.stat("n_instructions") / 10
     prep = emu_engine.compile(bundle.programs["prep"])
     assert prep.stat("n_levels") == 1  # every prepare instruction is independent
+
+
+@pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz"])
+def test_gradient_descent_iterates(emu_engine, golden, fixture):
+    import numpy as np
+    bundle = golden(fixture)
+    obj = parity.ExecutableObjective(emu_engine, bundle, 2)
+    lr = float(bundle.arrays["gd/learning_rate"][0])
+    state = {"x": bundle.arrays["x"].copy()}
+
+    def step():
+        loss, g = obj.evaluate(state["x"])
+        state["x"] = state["x"] + (-lr * g)
+        return loss, state["x"]
+
+    parity.check_gd_iterates(step, bundle)
