@@ -30,6 +30,7 @@ FRAMES = int(os.environ.get("BENCH_FRAMES", 256))
 LANES_PER_GPU = int(os.environ.get("BENCH_LANES", 1024))
 KIND = os.environ.get("BENCH_KIND", "handarm")
 HIDDEN = int(os.environ.get("BENCH_HIDDEN", 64))
+FUSE_DENSE = int(os.environ.get("BENCH_FUSE_DENSE", 1))
 MAX_DEVICE_BYTES = int(float(os.environ.get("BENCH_MAX_DEVICE_GB", 150)) * 1e9)
 CPU_SAMPLE_FRAMES = int(os.environ.get("BENCH_CPU_FRAMES", 16))
 CPU_SAMPLE_SECONDS = float(os.environ.get("BENCH_CPU_SECONDS", 12))
@@ -147,6 +148,7 @@ def workload_config(n_gpus):
         "frames": FRAMES, "rollouts_per_gpu": LANES_PER_GPU, "rollouts": LANES_PER_GPU * n_gpus,
         "parallelism": "rollouts sharded over %d GPU(s); all-reduce of {loss, gradient} per step" % n_gpus if n_gpus > 1
         else "single GPU",
+        "dense_layers": "one block instruction per layer (x_dense)" if FUSE_DENSE else "reference expansion (batch + dot4add per weight)",
         "l2": "working set (write-once tape image, tens of GB per chunk) is far larger than the 126 MB L2; no flush needed",
     }
 
@@ -173,7 +175,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_build = time.time()
-    bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop")
+    bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop", fuse_dense=FUSE_DENSE)
     engine = pkg.CudaEngine(local_rank)
     obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES)
     t_build = time.time() - t_build

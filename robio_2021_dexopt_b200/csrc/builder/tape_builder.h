@@ -39,6 +39,9 @@ class TapeBuilder {
 
   trxfile::Program prog;
   std::vector<uint64_t> frame_begin_inst;  // instruction count at frameBegin(t), before the passes
+  // record a dense layer as one block instruction (x_dense, vm_ops.def) instead of the reference's
+  // per-weight batch + dot4add expansion
+  bool fuse_dense = false;
 
  private:
   Alloc _alloc;
@@ -209,6 +212,7 @@ class TapeBuilder {
   // (dexopt/src/tensor.h:134-172 and dexopt/src/neural.h:176-181)
   std::vector<S> dense(const std::vector<S> &a, const std::vector<W> &wts, const std::vector<W> &bias, int n_in,
                        int n_out) {
+    if (fuse_dense) return denseFused(a, wts, bias, n_in, n_out);
     std::vector<S> r;
     S zero = cs(0.0);
     for (int col = 0; col < n_out; col++) {
@@ -230,6 +234,38 @@ class TapeBuilder {
       S bv = op1<S>("batch_8d", {bias[i].addr});
       r[i] = add(r[i], bv);
     }
+    return r;
+  }
+
+  // One instruction per layer: gather the activations into a contiguous block (plain moves), then
+  // x_dense on [x block, weight block, bias block] -> y block.  The weights of a layer are consecutive
+  // scalar input ports by construction (Assembler::initLayers).
+  std::vector<S> denseFused(const std::vector<S> &a, const std::vector<W> &wts, const std::vector<W> &bias, int n_in,
+                            int n_out) {
+    for (size_t k = 1; k < wts.size(); k++)
+      if (wts[k].addr != wts[0].addr + 8 * k) throw std::runtime_error("dense layer weights are not contiguous");
+    for (size_t k = 1; k < bias.size(); k++)
+      if (bias[k].addr != bias[0].addr + 8 * k) throw std::runtime_error("dense layer biases are not contiguous");
+    while (_alloc.top % 64) _alloc.top++;
+    uint64_t xb = _alloc.alloc((uint32_t)n_in * 64, L);
+    uint32_t mv = internOp(prog, _index, "move_8d");
+    for (int i = 0; i < n_in; i++) {
+      prog.code.push_back(mv);
+      prog.code.push_back(a[i].addr);
+      prog.code.push_back(xb + 64 * (uint64_t)i);
+      prog.n_instructions++;
+    }
+    uint64_t yb = _alloc.alloc((uint32_t)n_out * 64, L);
+    uint32_t id = internBlockOp(prog, _index, "x_dense_8d",
+                                {(uint32_t)n_in * 64, (uint32_t)(n_in * n_out) * 8, (uint32_t)n_out * 8, (uint32_t)n_out * 64});
+    prog.code.push_back(id);
+    prog.code.push_back(xb);
+    prog.code.push_back(wts[0].addr);
+    prog.code.push_back(bias[0].addr);
+    prog.code.push_back(yb);
+    prog.n_instructions++;
+    std::vector<S> r(n_out);
+    for (int j = 0; j < n_out; j++) r[j].addr = yb + 64 * (uint64_t)j;
     return r;
   }
 

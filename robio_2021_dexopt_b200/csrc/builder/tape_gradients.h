@@ -58,7 +58,8 @@ inline void packOffsets(std::vector<trxfile::Port> &ports) {
   }
 }
 
-inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
+// want_tangent = false skips fprop / hprop (block operators have no forward-mode variant yet)
+inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, bool want_tangent = true) {
   auto insts = decode(src);
   out = GradientPrograms();
   trxfile::Program &prep = out.prep, &fprop = out.fprop, &bprop = out.bprop, &hprop = out.hprop, &accu = out.accu;
@@ -101,6 +102,7 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
     }
     packOffsets(bprop.inputs);
     auto index = opIndex(bprop);
+    auto src_meta = opMeta(src);
     struct RInst {
       uint32_t op;
       std::vector<uint64_t> args;
@@ -112,7 +114,15 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
       std::string rname = variantName(src.ops[in.op].name, "reverse");
       if (!hasOp(rname)) throw std::runtime_error("variant not found: reverse " + src.ops[in.op].name);
       RInst r;
-      r.op = internOp(bprop, index, rname);
+      if (src_meta[in.op].sig->coop) {
+        // block operator: the reverse variant takes the original blocks, then their gradient blocks
+        std::vector<uint32_t> sizes;
+        for (int rep = 0; rep < 2; rep++)
+          for (uint32_t k = 0; k < in.n_args; k++) sizes.push_back(src.ops[in.op].args[k].size);
+        r.op = internBlockOp(bprop, index, rname, sizes);
+      } else {
+        r.op = internOp(bprop, index, rname);
+      }
       if (prep_at[i] < 0) {
         for (uint32_t k = 0; k < in.n_args; k++) r.args.push_back(src.code[in.code_at + k]);
       } else {
@@ -129,12 +139,39 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
     std::unordered_set<uint64_t> written;
     std::vector<RInst> acc;
     acc.reserve(rev.size() * 2);
+    std::vector<RInst> block_zeros;
     for (auto &r : rev) {
-      const auto &op = bprop.ops[r.op];
+      const auto op = bprop.ops[r.op];  // copy: internOp below may grow the table
+      uint16_t opcode;
+      uint32_t lw;
+      trx::findOp(op.name, opcode, lw);
+      const trx::OpSig &rsig = trx::opTable()[opcode];
       RInst main = r;
       std::vector<RInst> sums;
       for (size_t k = 0; k < r.args.size(); k++) {
         if (op.args[k].is_input) continue;
+        if (trx::isBlock(rsig.args[k].kind)) {
+          uint32_t eb = trx::blockElemBytes(rsig.args[k].kind, 8);
+          if (rsig.args[k].kind == trx::ARG_SA) {
+            // accumulated in place by the operator; zero it once before its first use, and make every
+            // later element-wise writer accumulate instead of overwrite
+            bool first = true;
+            for (uint32_t off = 0; off < op.args[k].size; off += eb)
+              if (written.count(r.args[k] + off)) first = false;
+            if (first) {
+              RInst z;
+              z.op = internBlockOp(bprop, index, "x_zero_block_d", {op.args[k].size});
+              z.args = {r.args[k]};
+              block_zeros.push_back(z);
+            }
+          } else {
+            for (uint32_t off = 0; off < op.args[k].size; off += eb)
+              if (written.count(r.args[k] + off))
+                throw std::runtime_error("block gradient written twice: fan-out of a dense-layer input block");
+          }
+          for (uint32_t off = 0; off < op.args[k].size; off += eb) written.insert(r.args[k] + off);
+          continue;
+        }
         if (written.count(r.args[k])) {
           uint64_t a = alloc.alloc(op.args[k].size, op.args[k].lanes);
           uint64_t b = alloc.alloc(op.args[k].size, op.args[k].lanes);
@@ -157,14 +194,34 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
     // zero prologue for gradient slots that are read before they are written (gradients.cpp:205-233)
     std::unordered_set<uint64_t> seen;
     for (auto &p : bprop.inputs) seen.insert(p.address);
-    std::vector<RInst> zeros;
+    for (auto &z : block_zeros)
+      for (uint32_t off = 0; off < bprop.ops[z.op].args[0].size; off += 8) seen.insert(z.args[0] + off);
+    std::vector<RInst> zeros = block_zeros;
     for (auto &r : acc) {
-      const auto &op = bprop.ops[r.op];
+      const auto op = bprop.ops[r.op];  // copy: internOp below may grow the table
+      uint16_t opcode;
+      uint32_t lw;
+      trx::findOp(op.name, opcode, lw);
+      const trx::OpSig &rsig = trx::opTable()[opcode];
       for (size_t k = 0; k < r.args.size(); k++) {
         if (r.args[k] < G) continue;
+        if (trx::isBlock(rsig.args[k].kind)) {
+          // element-wise: an element of a gradient block that nothing wrote before it is read is zero
+          uint32_t eb = trx::blockElemBytes(rsig.args[k].kind, 8);
+          for (uint32_t off = 0; off < op.args[k].size; off += eb)
+            if (seen.insert(r.args[k] + off).second && op.args[k].is_input) {
+              trxfile::ArgDesc ad;
+              ad.size = eb;
+              ad.lanes = (rsig.args[k].kind == trx::ARG_TB) ? 8 : 1;
+              RInst z;
+              z.op = internOp(bprop, index, typedOp("zero", ad));
+              z.args = {r.args[k] + off};
+              zeros.push_back(z);
+            }
+          continue;
+        }
         if (seen.insert(r.args[k]).second && op.args[k].is_input) {
           RInst z;
-          // note: op is re-fetched after internOp may have grown the table
           trxfile::ArgDesc ad = op.args[k];
           z.op = internOp(bprop, index, typedOp("zero", ad));
           z.args = {r.args[k]};
@@ -181,7 +238,7 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
   }
 
   // ---- fprop (gradients.cpp:236-316)
-  {
+  if (want_tangent) {
     for (auto p : src.inputs) {
       p.address += G;
       fprop.inputs.push_back(p);
@@ -224,7 +281,7 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
   }
 
   // ---- hprop = fprop ; bprop on one memory (gradients.cpp:344-362)
-  {
+  if (want_tangent) {
     hprop.inputs = fprop.inputs;
     hprop.outputs = bprop.outputs;
     auto index = opIndex(hprop);
@@ -247,7 +304,7 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out) {
       aa.push_back(p);
       accu.inputs.push_back(p);
     }
-    for (auto p : fprop.inputs) {
+    for (auto p : src.inputs) {  // the tangent ports (fprop.inputs) have the layout of the inputs
       p.address = alloc.alloc(p.size, p.lanes);
       bb.push_back(p);
       accu.inputs.push_back(p);

@@ -70,6 +70,62 @@ inline uint32_t internOp(trxfile::Program &p, std::map<std::string, uint32_t> &i
   return id;
 }
 
+// block operators (vm_ops.def, "product extensions") carry their block sizes in the operator table
+// entry, so every shape is its own entry; `sizes` = bytes per argument
+inline uint32_t internBlockOp(trxfile::Program &p, std::map<std::string, uint32_t> &index, const std::string &name,
+                              const std::vector<uint32_t> &sizes) {
+  std::string key = name;
+  for (auto s : sizes) key += "#" + std::to_string(s);
+  auto it = index.find(key);
+  if (it != index.end()) return it->second;
+  uint16_t opcode;
+  uint32_t lw;
+  if (!trx::findOp(name, opcode, lw)) throw std::runtime_error("operator not found: " + name);
+  const trx::OpSig &sig = trx::opTable()[opcode];
+  if (sig.args.size() != sizes.size()) throw std::runtime_error("block operator arity mismatch: " + name);
+  trxfile::OpDesc d;
+  d.name = name;
+  for (size_t k = 0; k < sizes.size(); k++) {
+    trxfile::ArgDesc ad;
+    ad.size = sizes[k];
+    ad.is_input = sig.args[k].is_input;
+    ad.lanes = (sig.args[k].kind == trx::ARG_TB) ? 8 : 1;
+    ad.elem = trxfile::ELEM_F64;
+    d.args.push_back(ad);
+  }
+  uint32_t id = (uint32_t)p.ops.size();
+  p.ops.push_back(d);
+  index[key] = id;
+  return id;
+}
+
+struct OpMeta {
+  uint16_t opcode = 0;
+  uint32_t lane_width = 1;
+  const trx::OpSig *sig = nullptr;
+};
+inline std::vector<OpMeta> opMeta(const trxfile::Program &p) {
+  std::vector<OpMeta> m(p.ops.size());
+  for (size_t i = 0; i < p.ops.size(); i++) {
+    if (!trx::findOp(p.ops[i].name, m[i].opcode, m[i].lane_width))
+      throw std::runtime_error("operator not found: " + p.ops[i].name);
+    m[i].sig = &trx::opTable()[m[i].opcode];
+  }
+  return m;
+}
+// calls f(address) for the argument's start address, or for every element of a block argument
+template <class F>
+inline void forEachKey(const trxfile::Program &p, const std::vector<OpMeta> &meta, const DecodedInst &in, uint32_t k, F f) {
+  const trx::ArgSig &a = meta[in.op].sig->args[k];
+  uint64_t addr = p.code[in.code_at + k];
+  if (!trx::isBlock(a.kind)) {
+    f(addr);
+    return;
+  }
+  uint32_t eb = trx::blockElemBytes(a.kind, 8), size = p.ops[in.op].args[k].size;
+  for (uint32_t off = 0; off < size; off += eb) f(addr + off);
+}
+
 inline std::map<std::string, uint32_t> opIndex(const trxfile::Program &p) {
   std::map<std::string, uint32_t> m;
   for (uint32_t i = 0; i < p.ops.size(); i++) m[p.ops[i].name] = i;
@@ -120,9 +176,10 @@ inline void foldConstants(trxfile::Program &p) {
   std::vector<uint64_t> code;
   code.reserve(p.code.size());
   uint64_t kept = 0;
+  auto meta = opMeta(p);
   for (auto &in : insts) {
     const auto &op = p.ops[in.op];
-    bool is_const = true;
+    bool is_const = !meta[in.op].sig->coop;
     for (uint32_t k = 0; k < in.n_args; k++)
       if (op.args[k].is_input && !values.count(p.code[in.code_at + k])) is_const = false;
     if (is_const) {
@@ -142,7 +199,7 @@ inline void foldConstants(trxfile::Program &p) {
         }
     } else {
       for (uint32_t k = 0; k < in.n_args; k++)
-        if (!op.args[k].is_input) values.erase(p.code[in.code_at + k]);
+        if (!op.args[k].is_input) forEachKey(p, meta, in, k, [&](uint64_t a) { values.erase(a); });
       code.push_back(in.op);
       for (uint32_t k = 0; k < in.n_args; k++) code.push_back(p.code[in.code_at + k]);
       kept++;
@@ -158,16 +215,17 @@ inline void removeUnused(trxfile::Program &p) {
   std::unordered_set<uint64_t> used;
   for (auto &o : p.outputs) used.insert(o.address);
   std::vector<uint8_t> keep(insts.size(), 0);
+  auto meta = opMeta(p);
   for (size_t i = insts.size(); i-- > 0;) {
     auto &in = insts[i];
     const auto &op = p.ops[in.op];
     bool op_used = false;
     for (uint32_t k = 0; k < in.n_args; k++)
-      if (!op.args[k].is_input && used.count(p.code[in.code_at + k])) op_used = true;
+      if (!op.args[k].is_input) forEachKey(p, meta, in, k, [&](uint64_t a) { if (used.count(a)) op_used = true; });
     if (!op_used) continue;
     keep[i] = 1;
     for (uint32_t k = 0; k < in.n_args; k++)
-      if (op.args[k].is_input) used.insert(p.code[in.code_at + k]);
+      if (op.args[k].is_input) forEachKey(p, meta, in, k, [&](uint64_t a) { used.insert(a); });
   }
   std::vector<uint64_t> code;
   uint64_t n = 0;

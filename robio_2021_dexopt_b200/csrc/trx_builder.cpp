@@ -20,7 +20,7 @@ extern "C" {
 const char *trx_builder_last_error(void) { return g_builder_error.c_str(); }
 
 // options: "key=value" pairs separated by spaces; keys: kind frames outer hidden dropout seed
-//          joints contacts extra_fixed wstd programs (comma separated subset of prog,prep,fprop,bprop,hprop,accu)
+//          joints contacts extra_fixed wstd fuse_dense programs (comma separated subset of prog,prep,fprop,bprop,hprop,accu)
 // On success *out points to a malloc'ed TRXB bundle (free with trx_builder_free) containing programs
 // prog/prep/fprop/bprop/hprop/accu, array "x" (initial policy parameters) and text "meta".
 int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
@@ -64,6 +64,7 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     for (auto &v : x0) v = wstd * rng.normal();
 
     trxb::TapeBuilder b;
+    b.fuse_dense = getI("fuse_dense", 0) != 0;
     {
       dexsyn::Assembler<trxb::TapeBuilder> as(b, model);
       for (int o = 0; o < outer; o++) as.rollout(frames, x0);
@@ -71,7 +72,9 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     uint64_t recorded = b.prog.n_instructions;
     b.finish();
     trxb::GradientPrograms g;
-    trxb::buildGradients(b.prog, g);
+    std::string want = "," + getS("programs", b.fuse_dense ? "prog,prep,bprop,accu" : "prog,prep,fprop,bprop,hprop,accu") + ",";
+    bool want_tangent = want.find(",fprop,") != std::string::npos || want.find(",hprop,") != std::string::npos;
+    trxb::buildGradients(b.prog, g, want_tangent);
 
     trxfile::Bundle bundle;
     std::string meta;
@@ -85,7 +88,6 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     meta += "n_joints=" + std::to_string(model.joints.size()) + "\n";
     meta += "n_end_effectors=" + std::to_string(model.end_effectors.size()) + "\n";
     bundle.texts.emplace_back("meta", meta);
-    std::string want = "," + getS("programs", "prog,prep,fprop,bprop,hprop,accu") + ",";
     auto put = [&](const char *name, trxfile::Program &p) {
       if (want.find(std::string(",") + name + ",") != std::string::npos) bundle.programs.emplace_back(name, std::move(p));
     };

@@ -65,6 +65,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
     const bool wide = (hdr >> 11) & 1u;
     const int nsub = (int)((hdr >> 12) & 31u) + 1;
     const int nargs = (int)((hdr >> 17) & 15u);
+    if ((hdr >> 21) & 1u) {
+      // block-cooperative record: every warp holds it at the same stream position
+      const uint32_t *next = pc + 1 + nargs + 2;
+      hdr = __ldg(next);
+      trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
+      pc = next;
+      continue;
+    }
     trxvm::Ctx c;
     c.m = m;
     int sub;

@@ -20,6 +20,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -29,9 +30,13 @@
 
 namespace trx {
 
+// record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21]
+//   bundle record:  header, then n_args x (4 | 32) argument words (slot index = byte address / 8)
+//   coop record:    header, then n_args argument words and two immediates; present in every warp's stream
 struct HeaderBits {
-  static uint32_t make(uint32_t opcode, bool wide, uint32_t n_sub, uint32_t n_args) {
-    return (opcode & 0x7ffu) | ((wide ? 1u : 0u) << 11) | (((n_sub - 1) & 31u) << 12) | ((n_args & 15u) << 17);
+  static uint32_t make(uint32_t opcode, bool wide, uint32_t n_sub, uint32_t n_args, bool coop = false) {
+    return (opcode & 0x7ffu) | ((wide ? 1u : 0u) << 11) | (((n_sub - 1) & 31u) << 12) | ((n_args & 15u) << 17) |
+           ((coop ? 1u : 0u) << 21);
   }
 };
 
@@ -120,11 +125,18 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       throw std::runtime_error("argument count mismatch for " + d.name);
     for (size_t k = 0; k < d.args.size(); k++) {
       const ArgSig &a = sig.args[k];
+      if (isBlock(a.kind)) {
+        uint32_t eb = blockElemBytes(a.kind, 8);
+        if (d.args[k].size == 0 || d.args[k].size % eb || (d.args[k].is_input != 0) != a.is_input)
+          throw std::runtime_error("block argument layout mismatch for " + d.name + " arg " + std::to_string(k));
+        continue;
+      }
       uint32_t expect_lanes = (a.kind == ARG_T) ? lw : 1;
       uint32_t expect_size = a.comps * 8 * expect_lanes;
       if (d.args[k].size != expect_size || (d.args[k].is_input != 0) != a.is_input || d.args[k].lanes != expect_lanes)
         throw std::runtime_error("argument layout mismatch for " + d.name + " arg " + std::to_string(k));
     }
+    if (sig.coop) tape_lanes = std::max<uint32_t>(tape_lanes, 8);
     ops[i] = {opcode, lw};
     tape_lanes = std::max(tape_lanes, lw);
     if (sig.mode == 'F') out.has_forward = true;
@@ -158,6 +170,17 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   out.n_instructions = insts.size();
 
   // ---- 3. levels (ASAP) with RAW / WAR / WAW edges keyed by argument start address
+  // an argument is tracked by its start address; block arguments by the start address of every element
+  auto forEachKey = [&](const Inst &in, size_t k, const std::function<void(uint64_t)> &f) {
+    const ArgSig &a = table[ops[in.op].opcode].args[k];
+    uint64_t addr = src.code[in.code_at + k];
+    if (!isBlock(a.kind)) {
+      f(addr);
+      return;
+    }
+    uint32_t eb = blockElemBytes(a.kind, 8), size = src.ops[in.op].args[k].size;
+    for (uint32_t off = 0; off < size; off += eb) f(addr + off);
+  };
   std::vector<uint64_t> addrs;
   addrs.reserve(src.code.size());
   for (auto &in : insts) {
@@ -165,8 +188,9 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     for (size_t k = 0; k < na; k++) {
       uint64_t a = src.code[in.code_at + k];
       if (a % 8) throw std::runtime_error("argument address not 8-byte aligned");
-      if (a >= src.memory_size) throw std::runtime_error("argument address outside the memory image");
-      addrs.push_back(a);
+      if (a + src.ops[in.op].args[k].size > src.memory_size)
+        throw std::runtime_error("argument address outside the memory image");
+      forEachKey(in, k, [&](uint64_t key) { addrs.push_back(key); });
     }
   }
   std::sort(addrs.begin(), addrs.end());
@@ -176,28 +200,34 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   };
   std::vector<uint32_t> wlevel(addrs.size(), 0), rlevel(addrs.size(), 0);
   uint32_t n_levels = 0;
-  std::vector<size_t> ids;
   for (auto &in : insts) {
     const OpSig &sig = table[ops[in.op].opcode];
     size_t na = sig.args.size();
-    ids.resize(na);
     uint32_t lvl = 0;
-    uint32_t lw = ops[in.op].lane_width;
     for (size_t k = 0; k < na; k++) {
-      ids[k] = slotId(src.code[in.code_at + k]);
-      if (sig.args[k].is_input) lvl = std::max(lvl, wlevel[ids[k]]);
-      else lvl = std::max(lvl, std::max(wlevel[ids[k]], rlevel[ids[k]]));
-      out.arg_bytes_per_tile += (uint64_t)sig.args[k].comps * 8 * (sig.args[k].kind == ARG_T ? lw : 1);
+      bool is_in = sig.args[k].is_input;
+      forEachKey(in, k, [&](uint64_t key) {
+        size_t id = slotId(key);
+        if (is_in) lvl = std::max(lvl, wlevel[id]);
+        else lvl = std::max(lvl, std::max(wlevel[id], rlevel[id]));
+      });
+      out.arg_bytes_per_tile += src.ops[in.op].args[k].size;
     }
     in.level = lvl + 1;
     n_levels = std::max(n_levels, in.level);
     for (size_t k = 0; k < na; k++)
-      if (sig.args[k].is_input) rlevel[ids[k]] = std::max(rlevel[ids[k]], in.level);
+      if (sig.args[k].is_input)
+        forEachKey(in, k, [&](uint64_t key) {
+          size_t id = slotId(key);
+          rlevel[id] = std::max(rlevel[id], in.level);
+        });
     for (size_t k = 0; k < na; k++)
-      if (!sig.args[k].is_input) {
-        wlevel[ids[k]] = in.level;
-        rlevel[ids[k]] = in.level;
-      }
+      if (!sig.args[k].is_input)
+        forEachKey(in, k, [&](uint64_t key) {
+          size_t id = slotId(key);
+          wlevel[id] = in.level;
+          rlevel[id] = in.level;
+        });
   }
   out.n_levels = n_levels;
 
@@ -230,6 +260,36 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       return oa.lane_width < ob.lane_width;
     });
     bundles.clear();
+    // block-cooperative instructions first: one record, replicated into every warp's stream
+    for (size_t i = 0; i < lvl_insts.size(); i++) {
+      const Inst &in = insts[lvl_insts[i]];
+      const OpRef &o = ops[in.op];
+      const OpSig &sig = table[o.opcode];
+      if (!sig.coop) continue;
+      const auto &d = src.ops[in.op];
+      uint32_t imm0 = 0, imm1 = 0;
+      if (o.opcode == OP_X_DENSE || o.opcode == OP_R_X_DENSE) {
+        imm0 = d.args[0].size / 64;
+        imm1 = d.args[3].size / 64;
+        if (d.args[1].size != (uint64_t)imm0 * imm1 * 8 || d.args[2].size != imm1 * 8)
+          throw std::runtime_error("dense layer block sizes are inconsistent");
+      } else if (o.opcode == OP_X_ZERO_BLOCK) {
+        imm0 = d.args[0].size / 8;
+      } else {
+        throw std::runtime_error("unknown block operator " + d.name);
+      }
+      uint32_t na = (uint32_t)sig.args.size();
+      for (auto &s : streams) {
+        s.push_back(HeaderBits::make(o.opcode, false, 1, na, true));
+        for (uint32_t k = 0; k < na; k++) s.push_back((uint32_t)(src.code[in.code_at + k] / 8));
+        s.push_back(imm0);
+        s.push_back(imm1);
+      }
+      out.n_bundles++;
+    }
+    lvl_insts.erase(std::remove_if(lvl_insts.begin(), lvl_insts.end(),
+                                   [&](uint32_t i) { return table[ops[insts[i].op].opcode].coop; }),
+                    lvl_insts.end());
     for (size_t i = 0; i < lvl_insts.size();) {
       const OpRef &o = ops[insts[lvl_insts[i]].op];
       bool wide = (o.lane_width == 1);

@@ -22,7 +22,10 @@ enum Opcode : uint16_t {
   OP_END = 0x7ff
 };
 
-enum ArgKind : uint8_t { ARG_T = 0, ARG_S = 1, ARG_U = 2 };
+// ARG_T lane-typed value, ARG_S BatchScalar, ARG_U uint64 handle; block kinds (components = 0 in the
+// signature, the size comes from the program's operator table): ARG_TB contiguous lane-typed slots,
+// ARG_SB contiguous scalar slots, ARG_SA scalar block that the operator accumulates into (+=)
+enum ArgKind : uint8_t { ARG_T = 0, ARG_S = 1, ARG_U = 2, ARG_TB = 3, ARG_SB = 4, ARG_SA = 5 };
 
 struct ArgSig {
   bool is_input;
@@ -37,6 +40,7 @@ struct OpSig {
   std::vector<ArgSig> args;
   std::string tape_name;  // "[mode_]base"
   unsigned cost = 0;      // components moved, used for load balancing
+  bool coop = false;      // block-cooperative operator (has block arguments)
 };
 
 inline const std::vector<OpSig> &opTable() {
@@ -53,12 +57,13 @@ inline const std::vector<OpSig> &opTable() {
         ArgSig a;
         a.is_input = (*p++ == 'i');
         char k = *p++;
-        a.kind = (k == 'T') ? ARG_T : (k == 'S') ? ARG_S : ARG_U;
+        a.kind = (k == 'T') ? ARG_T : (k == 'S') ? ARG_S : (k == 'B') ? ARG_TB : (k == 'C') ? ARG_SB : (k == 'A') ? ARG_SA : ARG_U;
         int n = 0;
         while (*p >= '0' && *p <= '9') n = n * 10 + (*p++ - '0');
         a.comps = (uint8_t)n;
         op.args.push_back(a);
         op.cost += (unsigned)n;
+        if (a.kind >= ARG_TB) op.coop = true;
       }
       const char *prefix = op.mode == 'P' ? "prepare_" : op.mode == 'F' ? "forward_" : op.mode == 'R' ? "reverse_" : "";
       op.tape_name = std::string(prefix) + op.base;
@@ -67,6 +72,10 @@ inline const std::vector<OpSig> &opTable() {
   }();
   return table;
 }
+
+inline bool isBlock(ArgKind k) { return k >= ARG_TB; }
+// bytes per element of a block argument
+inline uint32_t blockElemBytes(ArgKind k, uint32_t lane_width) { return k == ARG_TB ? 8 * lane_width : 8; }
 
 // "prepare_mul_fg_pose_8d" -> (opcode, lane width); returns false if unknown
 inline bool findOp(const std::string &tape_name, uint16_t &opcode, uint32_t &lane_width) {

@@ -84,4 +84,61 @@ TRX_HD void exec(uint32_t opcode, const Ctx &c) {
   }
 }
 
+
+// Block-cooperative operators.  `a` = argument words (slot indices in doubles) followed by the two
+// immediates n_in, n_out; thread `tid` of `nthreads` takes a strided share of the work.
+TRX_HD void exec_coop(uint32_t opcode, const uint32_t *a, double *m, int tid, int nthreads) {
+  switch (opcode) {
+    case trx::OP_X_DENSE: {
+      const double *x = m + a[0], *W = m + a[1], *b = m + a[2];
+      double *y = m + a[3];
+      const int n_in = (int)a[4], n_out = (int)a[5];
+      for (int o = tid; o < n_out * 8; o += nthreads) {
+        const int j = o >> 3, lane = o & 7;
+        double acc = 0.0;
+        int row = 0;
+        // tensor.h:147-159: rows in groups of four through dot4add, then madd for the tail
+        for (; row + 3 < n_in; row += 4) {
+          acc = x[(row + 0) * 8 + lane] * W[(row + 0) * n_out + j] + x[(row + 1) * 8 + lane] * W[(row + 1) * n_out + j] +
+                x[(row + 2) * 8 + lane] * W[(row + 2) * n_out + j] + x[(row + 3) * 8 + lane] * W[(row + 3) * n_out + j] + acc;
+        }
+        for (; row < n_in; row++) acc = x[row * 8 + lane] * W[row * n_out + j] + acc;
+        y[j * 8 + lane] = acc + b[j];  // neural.h:176-181
+      }
+    } break;
+    case trx::OP_R_X_DENSE: {
+      const double *x = m + a[0], *W = m + a[1];
+      double *gx = m + a[4], *gW = m + a[5], *gb = m + a[6];
+      const double *gy = m + a[7];
+      const int n_in = (int)a[8], n_out = (int)a[9];
+      // gx[i] = sum_j gy[j] * W[i][j]
+      for (int o = tid; o < n_in * 8; o += nthreads) {
+        const int i = o >> 3, lane = o & 7;
+        double acc = 0.0;
+        for (int j = 0; j < n_out; j++) acc += gy[j * 8 + lane] * W[i * n_out + j];
+        gx[i * 8 + lane] = acc;
+      }
+      // gW[i][j] += sum over lanes (left to right, as reverse_batch) of x[i] * gy[j]
+      for (int e = tid; e < n_in * n_out; e += nthreads) {
+        const int i = e / n_out, j = e - i * n_out;
+        double rs = 0.0;
+        for (int lane = 0; lane < 8; lane++) rs += gy[j * 8 + lane] * x[i * 8 + lane];
+        gW[e] += rs;
+      }
+      for (int j = tid; j < n_out; j += nthreads) {
+        double rs = 0.0;
+        for (int lane = 0; lane < 8; lane++) rs += gy[j * 8 + lane];
+        gb[j] += rs;
+      }
+    } break;
+    case trx::OP_X_ZERO_BLOCK: {
+      double *z = m + a[0];
+      const int n = (int)a[1];
+      for (int e = tid; e < n; e += nthreads) z[e] = 0.0;
+    } break;
+    default:
+      break;
+  }
+}
+
 }  // namespace trxvm

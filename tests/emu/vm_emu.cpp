@@ -167,6 +167,13 @@ int emu_execute(const emu_program *p, emu_memory *m) {
           bool wide = (hdr >> 11) & 1u;
           int nsub = (int)((hdr >> 12) & 31u) + 1;
           int nargs = (int)((hdr >> 17) & 15u);
+          if ((hdr >> 21) & 1u) {
+            // block-cooperative record: this warp's 32 threads do their share
+            for (int lane32 = 0; lane32 < 32; lane32++)
+              trxvm::exec_coop(op, pc[w] + 1, mem, (int)(w * 32 + lane32), (int)(W * 32));
+            pc[w] += 1 + nargs + 2;
+            continue;
+          }
           for (int lane32 = 0; lane32 < 32; lane32++) {
             trxvm::Ctx c;
             c.m = mem;

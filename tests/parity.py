@@ -64,8 +64,6 @@ def tile_arrays(bundle, key):
 def check_problem(engine, bundle, n_tiles=None, check_tangent=True):
     """objective + gradient over several lane tiles: x_prog, x_prep, x_bprop as in solvers/gd.h:50-63"""
     prog = bundle.view("prog")
-    bprop = bundle.view("bprop")
-    fprop = bundle.view("fprop")
     params = tile_arrays(bundle, "params")
     r_ref = tile_arrays(bundle, "r")
     if n_tiles is None:
@@ -93,6 +91,7 @@ def check_problem(engine, bundle, n_tiles=None, check_tangent=True):
     elif n_tiles == 1:
         assert_close(g, bundle.arrays["tile0/g"], "gradient (tile 0)")
     if check_tangent:
+        fprop = bundle.view("fprop")
         x_fprop = engine.compile(bundle.programs["fprop"])
         dr = x_fprop.run(bundle.arrays["dx"], mem)
         dr_want = trxfile.tiles_to_wide(fprop.outputs, tile_arrays(bundle, "dr")[:n_tiles])

@@ -47,12 +47,16 @@ def test_recorded_tape_equals_reference_recording(golden, fixture, options):
 
 
 @pytest.mark.parametrize("fixture,options", CASES)
-def test_built_programs_reproduce_reference_numbers(emu_engine, golden, fixture, options):
-    """residuals, loss, gradient and tangent of the product-built prog/prep/bprop/fprop equal the
-    reference engine's results on the reference-recorded tape"""
+@pytest.mark.parametrize("fuse_dense", [0, 1])
+def test_built_programs_reproduce_reference_numbers(emu_engine, golden, fixture, options, fuse_dense):
+    """residuals, loss, gradient (and tangent) of the product-built programs equal the reference engine's
+    results on the reference-recorded tape; fuse_dense=1 records dense layers as block instructions"""
     import robio_2021_dexopt_b200 as pkg
     ref = golden(fixture)
-    mine = pkg.build_dexsyn(**options)
+    mine = pkg.build_dexsyn(fuse_dense=fuse_dense, **options)
     for k, v in ref.arrays.items():
         mine.arrays.setdefault(k, v)
-    parity.check_problem(emu_engine, mine)
+    parity.check_problem(emu_engine, mine, check_tangent=not fuse_dense)
+    if fuse_dense:
+        n_ref = int(ref.meta()["n_prog_instructions"])
+        assert int(mine.meta()["n_prog_instructions"]) < 0.7 * n_ref
