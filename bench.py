@@ -31,6 +31,7 @@ LANES_PER_GPU = int(os.environ.get("BENCH_LANES", 1024))
 KIND = os.environ.get("BENCH_KIND", "handarm")
 HIDDEN = int(os.environ.get("BENCH_HIDDEN", 64))
 FUSE_DENSE = int(os.environ.get("BENCH_FUSE_DENSE", 1))
+FUSED = int(os.environ.get("BENCH_FUSED", 1))
 MAX_DEVICE_BYTES = int(float(os.environ.get("BENCH_MAX_DEVICE_GB", 150)) * 1e9)
 CPU_SAMPLE_FRAMES = int(os.environ.get("BENCH_CPU_FRAMES", 16))
 CPU_SAMPLE_SECONDS = float(os.environ.get("BENCH_CPU_SECONDS", 12))
@@ -177,7 +178,7 @@ def main():
     t_build = time.time()
     bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop", fuse_dense=FUSE_DENSE)
     engine = pkg.CudaEngine(local_rank)
-    obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES)
+    obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES, fused=bool(FUSED))
     t_build = time.time() - t_build
     n_x = obj.n_x
     prog = bundle.view("prog")
@@ -269,9 +270,8 @@ def main():
     units_per_launch = FRAMES * obj.info("chunk_lanes")
     # the adjoint kernel's share of the algorithmic bytes: it must read the per-frame state once (B_ALG / 2)
     achieved = (B_ALG / 2) * units_per_launch / (bprop_ms_per_launch * 1e-3) / 1e9
-    tape_bytes = sum(engine_stat for engine_stat in (obj.x_prog.stat("arg_bytes_per_tile"),
-                                                     obj.x_prep.stat("arg_bytes_per_tile"),
-                                                     obj.x_bprop.stat("arg_bytes_per_tile")))
+    tape_bytes = obj.info("prog.arg_bytes_per_tile") + obj.info("prep.arg_bytes_per_tile") + obj.info(
+        "bprop.arg_bytes_per_tile")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,7 +281,7 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "trx_vm_kernel (bprop launch)", "peak_source": peak_source,
+            "kernel": "trx_vm_kernel (adjoint launch)", "lowering": "fused (chain schedule + slot rings)" if FUSED else "generic (levels)", "peak_source": peak_source,
             "algorithmic_bytes_per_unit": B_ALG / 2, "units_per_launch": units_per_launch,
             "launch_ms": bprop_ms_per_launch,
             "kernel_ms_per_step": {"prog": kernel_ms[0] / args.steps, "prep_seed": kernel_ms[1] / args.steps,

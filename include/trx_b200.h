@@ -173,12 +173,18 @@ trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void 
  *     x_prog->run(x, mem, r);  loss = r.squaredNorm();  x_prep->execute(mem);  x_bprop->run(r, mem, g);
  * with r kept on the device.  `lanes` rollouts are evaluated; if their write-once memory images
  * exceed `max_device_bytes` (0 = no limit) the rollouts are walked in equal chunks and the
- * gradients summed (rollouts are independent).  The programs must outlive the objective. */
+ * gradients summed (rollouts are independent). */
 typedef struct trx_objective trx_objective;
-trx_status trx_objective_create(const trx_program *prog, const trx_program *prep, const trx_program *bprop,
-                                uint64_t lanes, uint64_t max_device_bytes, int device, trx_objective **out);
+/* flags: TRX_OBJECTIVE_FUSED lowers forward+prepare and the adjoint with chain scheduling and on-chip
+ * slot rings (csrc/trx_fuse.h) instead of as three generic executables.  The three programs are given
+ * as TRXB program payloads (include/trx_file.h); the objective owns everything it builds from them. */
+enum { TRX_OBJECTIVE_FUSED = 1 };
+trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
+                                const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
+                                int device, int flags, trx_objective **out);
 void trx_objective_destroy(trx_objective *o);
-/* keys: n_x lanes chunk_lanes n_chunks parameter_bytes device_bytes launches_per_evaluation */
+/* keys: n_x lanes chunk_lanes n_chunks parameter_bytes device_bytes launches_per_evaluation fused,
+ * and prog.<stat> / prep.<stat> / bprop.<stat> with the keys of trx_program_stat */
 trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t *value);
 /* per-lane parameters of all rollouts, wide layout, host pointer (Executable::parameterize) */
 trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint64_t bytes, void *stream);

@@ -53,8 +53,8 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
     L.trx_execute.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     L.trx_memory_peek.argtypes = [c.c_void_p, c.c_uint64, c.c_uint64, c.c_void_p, c.c_uint64]
-    L.trx_objective_create.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_uint64, c.c_int,
-                                       c.POINTER(c.c_void_p)]
+    L.trx_objective_create.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t,
+                                       c.c_uint64, c.c_uint64, c.c_int, c.c_int, c.POINTER(c.c_void_p)]
     L.trx_objective_destroy.argtypes = [c.c_void_p]
     L.trx_objective_destroy.restype = None
     L.trx_objective_info.argtypes = [c.c_void_p, c.c_char_p, c.POINTER(c.c_uint64)]

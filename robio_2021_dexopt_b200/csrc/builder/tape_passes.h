@@ -152,6 +152,9 @@ inline void hostExec(const trxfile::Program &p, const DecodedInst &in,
   for (int lane = 0; lane < (lw == 1 ? 1 : 8); lane++) {
     trxvm::Ctx c;
     c.m = scratch.data();
+    c.ring = nullptr;
+    c.nargs = (int)in.n_args;
+    c.dual = false;
     c.a = args;
     c.as = 1;
     c.cs = (lw == 1) ? 1 : 8;

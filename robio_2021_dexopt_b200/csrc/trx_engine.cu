@@ -22,6 +22,7 @@
 
 #include "../../include/trx_b200.h"
 #include "trx_lower.h"
+#include "trx_fuse.h"
 #include "vm_exec.cuh"
 
 namespace {
@@ -43,16 +44,21 @@ trx_status fail(trx_status code, const std::string &msg) {
 
 // ------------------------------------------------------------------ kernels
 
-// The interpreter.  grid = tiles, block = W warps.
+// The interpreter.  grid = tiles, block = W warps; dynamic shared memory = W slot rings.
+// record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21] | dual[22]
 template <int kMaxWarps>
 __global__ void __launch_bounds__(kMaxWarps * 32)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
-                  uint64_t tile_stride) {
+                  uint64_t tile_stride, uint32_t ring_doubles) {
+  extern __shared__ double trx_rings[];
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
   const int lane32 = threadIdx.x & 31;
   const uint32_t *pc = stream + stream_begin[warp];
   uint32_t hdr = __ldg(pc);
+  trxvm::Ctx c;
+  c.m = m;
+  c.ring = trx_rings + (size_t)warp * ring_doubles;
   while (true) {
     const uint32_t op = hdr & 0x7ffu;
     if (op == trx::OP_END) break;
@@ -73,8 +79,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       pc = next;
       continue;
     }
-    trxvm::Ctx c;
-    c.m = m;
+    c.dual = (hdr >> 22) & 1u;
+    c.nargs = nargs;
     int sub;
     if (wide) {
       sub = lane32;
@@ -88,9 +94,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       c.lo = lane32 & 7;
     }
     c.a = pc + 1 + sub;
-    const uint32_t *next = pc + 1 + nargs * c.as;
+    const uint32_t *next = pc + 1 + (c.dual ? 2 * nargs : nargs) * c.as;
     hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
+    // pull the lines of the following record(s) towards L1 while this one executes
+    if (lane32 < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
     if (sub < nsub) trxvm::exec(op, c);
+    __syncwarp();  // ring slots written by one quarter-warp may be read by another in the next record
     pc = next;
   }
 }
@@ -337,6 +346,10 @@ const char *trx_op_signature(int i) {
 
 uint64_t trx_kernel_launch_count(void) { return g_launches.load(); }
 
+// uploads p->low (already lowered) to the device
+static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int scalar_in, int scalar_out,
+                                trx_program **out);
+
 static trx_status createFromFile(const trxfile::Program &src, int device, int scalar_in, int scalar_out,
                                  trx_program **out) {
   if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
@@ -352,6 +365,11 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     bool unsupported = msg.find("unsupported operator") != std::string::npos;
     return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, msg);
   }
+  return finishProgram(p, device, scalar_in, scalar_out, out);
+}
+
+static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int scalar_in, int scalar_out,
+                                trx_program **out) {
   // scalar-typed port behaviour across tiles (see trx_b200.h)
   bool reverse_only = p->low.has_reverse && !p->low.has_forward;
   p->scalar_inputs = scalar_in != TRX_SCALAR_AUTO ? scalar_in : (reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED);
@@ -451,6 +469,12 @@ trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *val
   else if (k == "arg_bytes_per_tile") *value = p->low.arg_bytes_per_tile;
   else if (k == "max_level_width") *value = p->low.max_level_width;
   else if (k == "n_constants") *value = p->low.const_idx.size();
+  else if (k == "ring_doubles") *value = p->low.ring_doubles;
+  else if (k == "n_ring_reads") *value = p->low.n_ring_reads;
+  else if (k == "n_image_reads") *value = p->low.n_image_reads;
+  else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;
+  else if (k == "n_dual_writes") *value = p->low.n_dual_writes;
+  else if (k == "n_image_writes") *value = p->low.n_image_writes;
   else if (k == "scalar_inputs") *value = (uint64_t)p->scalar_inputs;
   else if (k == "scalar_outputs") *value = (uint64_t)p->scalar_outputs;
   else return fail(TRX_ERR_INVALID, "unknown statistic " + k);
@@ -528,8 +552,14 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
   }
   if (p->low.n_instructions) {
     uint32_t W = p->low.n_warps;
-    trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                m->tile_stride);
+    size_t smem = (size_t)W * p->low.ring_doubles * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                   m->tile_stride, p->low.ring_doubles);
     g_launches++;
   }
   TRX_CUDA(cudaGetLastError());
@@ -592,7 +622,10 @@ trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void 
 // ------------------------------------------------------------------ objective (solver-level glue)
 
 struct trx_objective {
-  const trx_program *prog = nullptr, *prep = nullptr, *bprop = nullptr;
+  // owned.  fused: prog = forward+prepare, prep = null, bprop = adjoint (trx_fuse.h);
+  // otherwise the three programs lowered one by one as generic executables (trx_lower.h)
+  trx_program *prog = nullptr, *prep = nullptr, *bprop = nullptr;
+  bool fused = false;
   int device = 0;
   uint64_t lanes = 0, chunk_lanes = 0, n_chunks = 0;
   uint64_t n_x = 0;
@@ -613,11 +646,61 @@ struct trx_objective {
 
 extern "C" {
 
-trx_status trx_objective_create(const trx_program *prog, const trx_program *prep, const trx_program *bprop,
-                                uint64_t lanes, uint64_t max_device_bytes, int device, trx_objective **out) {
-  if (!prog || !prep || !bprop || !out) return fail(TRX_ERR_INVALID, "bad argument");
+// Fused lowering of the objective's two sweeps (trx_fuse.h)
+static trx_status lowerObjectiveFused(const trxfile::Program &prog, const trxfile::Program &prep,
+                                      const trxfile::Program &bprop, std::unique_ptr<trx_program> &fwd,
+                                      std::unique_ptr<trx_program> &adj) {
+  try {
+    trx::FuseOptions opt;
+    if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_RING_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_SYNC_PENALTY")) opt.sync_penalty = (uint32_t)atoi(w);
+    trx::lowerObjective(prog, prep, bprop, opt, fwd->low, adj->low);
+  } catch (const std::exception &e) {
+    std::string msg = e.what();
+    bool unsupported = msg.find("unsupported operator") != std::string::npos;
+    return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, msg);
+  }
+  return TRX_OK;
+}
+
+trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
+                                const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
+                                int device, int flags, trx_objective **out) {
+  if (!prog_blob || !prep_blob || !bprop_blob || !out) return fail(TRX_ERR_INVALID, "bad argument");
   *out = nullptr;
   if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
+  std::unique_ptr<trx_objective> o(new trx_objective());
+  o->fused = (flags & TRX_OBJECTIVE_FUSED) != 0;
+  {
+    trxfile::Program p_prog, p_prep, p_bprop;
+    try {
+      trxfile::decodeProgram(prog_blob, prog_bytes, p_prog);
+      trxfile::decodeProgram(prep_blob, prep_bytes, p_prep);
+      trxfile::decodeProgram(bprop_blob, bprop_bytes, p_bprop);
+    } catch (const std::exception &e) {
+      return fail(TRX_ERR_INVALID, e.what());
+    }
+    trx_status s;
+    trx_program *raw = nullptr;
+    if (o->fused) {
+      std::unique_ptr<trx_program> fwd(new trx_program()), adj(new trx_program());
+      if ((s = lowerObjectiveFused(p_prog, p_prep, p_bprop, fwd, adj)) != TRX_OK) return s;
+      if ((s = finishProgram(fwd, device, TRX_SCALAR_SHARED, TRX_SCALAR_SHARED, &raw)) != TRX_OK) return s;
+      o->prog = raw;
+      if ((s = finishProgram(adj, device, TRX_SCALAR_REDUCE, TRX_SCALAR_REDUCE, &raw)) != TRX_OK) return s;
+      o->bprop = raw;
+      o->prep = nullptr;
+    } else {
+      if ((s = createFromFile(p_prog, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      o->prog = raw;
+      if ((s = createFromFile(p_prep, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      o->prep = raw;
+      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      o->bprop = raw;
+    }
+  }
+  const trx_program *prog = o->prog, *prep = o->prep, *bprop = o->bprop;
   const auto &po = prog->low.outputs.elems;
   const auto &bi = bprop->low.inputs.elems;
   if (po.size() != bi.size()) return fail(TRX_ERR_INVALID, "bprop inputs do not mirror prog outputs");
@@ -626,16 +709,12 @@ trx_status trx_objective_create(const trx_program *prog, const trx_program *prep
   if (bprop->low.outputs.elems.size() != prog->low.inputs.elems.size())
     return fail(TRX_ERR_INVALID, "bprop outputs do not mirror prog inputs");
   TRX_CUDA(cudaSetDevice(device));
-  std::unique_ptr<trx_objective> o(new trx_objective());
-  o->prog = prog;
-  o->prep = prep;
-  o->bprop = bprop;
   o->device = device;
   o->lanes = lanes;
   o->n_x = prog->low.inputs.elems.size();
   // lane chunking: rollouts are independent, so when the write-once memory image of all tiles does
   // not fit the budget the tiles are evaluated in equal chunks and the gradients summed
-  uint64_t per_tile = std::max(std::max(prog->low.memory_size, prep->low.memory_size), bprop->low.memory_size);
+  uint64_t per_tile = std::max(std::max(prog->low.memory_size, prep ? prep->low.memory_size : 0), bprop->low.memory_size);
   uint64_t tiles = lanes / 8;
   uint64_t budget_tiles = max_device_bytes ? std::max<uint64_t>(1, max_device_bytes / per_tile) : tiles;
   uint64_t chunk_tiles = std::min(tiles, budget_tiles);
@@ -668,6 +747,9 @@ trx_status trx_objective_create(const trx_program *prog, const trx_program *prep
 
 void trx_objective_destroy(trx_objective *o) {
   if (!o) return;
+  trx_program_destroy(o->prog);
+  trx_program_destroy(o->prep);
+  trx_program_destroy(o->bprop);
   trx_memory_destroy(o->mem);
   cudaFree(o->d_x);
   cudaFree(o->d_params);
@@ -691,13 +773,20 @@ trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t 
   else if (k == "n_chunks") *value = o->n_chunks;
   else if (k == "parameter_bytes") *value = o->param_elems * 8;
   else if (k == "device_bytes") *value = o->mem->tile_stride * o->mem->n_tiles * 8;
+  else if (k == "fused") *value = o->fused ? 1 : 0;
+  else if (k.rfind("prog.", 0) == 0) return trx_program_stat(o->prog, key + 5, value);
+  else if (k.rfind("prep.", 0) == 0) {
+    if (!o->prep) { *value = 0; return TRX_OK; }
+    return trx_program_stat(o->prep, key + 5, value);
+  }
+  else if (k.rfind("bprop.", 0) == 0) return trx_program_stat(o->bprop, key + 6, value);
   else if (k == "launches_per_evaluation") {
     uint64_t per_chunk = 0;
     per_chunk += o->param_elems ? 1 : 0;                       // parameter scatter
     per_chunk += 1;                                            // input scatter
     per_chunk += (o->prog->low.const_idx.empty() ? 0 : 1) + 1; // prog
     per_chunk += 1;                                            // seed
-    per_chunk += (o->prep->low.n_instructions ? 1 : 0);        // prep
+    per_chunk += (o->prep && o->prep->low.n_instructions ? 1 : 0);  // prep
     per_chunk += (o->bprop->low.n_instructions ? 1 : 0);       // bprop
     per_chunk += 1;                                            // gradient gather
     *value = per_chunk * o->n_chunks + 1;
@@ -745,7 +834,7 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
     trx_seed_kernel<<<(unsigned)chunk_tiles, 256, 0, stream>>>(o->d_seed, o->n_seed, m->d_mem, m->tile_stride,
                                                               c == 0 ? 1 : 0, o->d_partial + c * chunk_tiles);
     g_launches++;
-    if ((s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
+    if (o->prep && (s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[2], stream);
     if ((s = trx_execute(o->bprop, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[3], stream);

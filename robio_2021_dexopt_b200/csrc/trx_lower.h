@@ -93,6 +93,8 @@ struct LoweredProgram {
   uint64_t n_instructions = 0, n_levels = 0, n_bundles = 0;
   uint64_t arg_bytes_per_tile = 0;
   uint64_t max_level_width = 0;
+  uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
+  uint64_t n_ring_reads = 0, n_image_reads = 0, n_ring_only_writes = 0, n_dual_writes = 0, n_image_writes = 0;
   bool has_forward = false, has_reverse = false;
   PortLayout inputs, parameters, outputs;
   std::vector<uint32_t> const_idx;

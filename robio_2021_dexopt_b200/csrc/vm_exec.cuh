@@ -14,27 +14,44 @@
 
 namespace trxvm {
 
+// Argument words.  bit 31 set: the value lives in this warp's on-chip slot ring (shared memory),
+// bits [0,16) = offset in doubles; otherwise the word is the slot index (byte address / 8) in the
+// tile's memory image.  "dual" records carry a second row of words per argument: the memory-image
+// index an output is written to in addition to its ring slot (kNoSlot = none).
+static constexpr uint32_t kRingFlag = 0x80000000u;
+static constexpr uint32_t kNoSlot = 0xffffffffu;
+
 struct Ctx {
-  double *m;           // base of this tile's memory image
+  double *m;           // base of this tile's memory image (global memory)
+  double *ring;        // base of this warp's slot ring (shared memory)
   const uint32_t *a;   // first argument word of this thread's sub-instruction
   int as;              // stride between consecutive arguments in the record (4 or 32)
   int cs;              // component stride in doubles (8 lane-typed, 1 scalar)
   int lo;              // lane offset (0..7)
+  int nargs;           // number of arguments (rows) of the record
+  bool dual;           // record has a second row of words per argument
 };
 
-TRX_HD uint32_t argbase(const Ctx &c, int k) { return c.a[k * c.as]; }
-TRX_HD double ld(const Ctx &c, int k, int j) { return c.m[argbase(c, k) + j * c.cs + c.lo]; }
-TRX_HD void st(const Ctx &c, int k, int j, double v) { c.m[argbase(c, k) + j * c.cs + c.lo] = v; }
-// BatchScalar-typed argument: one double shared by the lanes
-TRX_HD double lds(const Ctx &c, int k) { return c.m[argbase(c, k)]; }
+TRX_HD uint32_t argword(const Ctx &c, int k) { return c.a[k * c.as]; }
+TRX_HD double *slotptr(const Ctx &c, uint32_t w) { return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w); }
+TRX_HD double ld(const Ctx &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.cs + c.lo]; }
+TRX_HD void st(const Ctx &c, int k, int j, double v) {
+  slotptr(c, argword(c, k))[j * c.cs + c.lo] = v;
+  if (c.dual) {
+    uint32_t w2 = c.a[(c.nargs + k) * c.as];
+    if (w2 != kNoSlot) c.m[w2 + j * c.cs + c.lo] = v;
+  }
+}
+// BatchScalar-typed argument: one double shared by the lanes (always in the memory image)
+TRX_HD double lds(const Ctx &c, int k) { return c.m[argword(c, k)]; }
 // reverse of `batch`: da = sum of the lanes of dx, left to right (dexopt/src/ops.h:22-30)
 TRX_HD void sts_lanesum(const Ctx &c, int kout, int kin) {
   if (c.lo != 0) return;
-  const double *p = c.m + argbase(c, kin);
+  const double *p = slotptr(c, argword(c, kin));
   double rs = 0.0;
   int n = (c.cs == 8) ? 8 : 1;
   for (int i = 0; i < n; i++) rs += p[i];
-  c.m[argbase(c, kout)] = rs;
+  c.m[argword(c, kout)] = rs;
 }
 TRX_HD V3 ldv(const Ctx &c, int k, int o) { return V3{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2)}; }
 TRX_HD Q4 ldq(const Ctx &c, int k, int o) { return Q4{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2), ld(c, k, o + 3)}; }

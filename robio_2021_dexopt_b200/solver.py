@@ -23,14 +23,17 @@ from .engine import CudaEngine
 class Objective:
     """objective + gradient over R rollouts of a recorded problem (prog/prep/bprop of one bundle)"""
 
-    def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0):
+    def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0,
+                 fused: bool = True):
+        """fused=True: forward+prepare and adjoint lowered with chain scheduling and on-chip slot rings
+        (csrc/trx_fuse.h); fused=False: the three programs as generic executables (csrc/trx_lower.h)"""
         self.engine = engine
-        self.x_prog = engine.compile(bundle.programs["prog"])
-        self.x_prep = engine.compile(bundle.programs["prep"])
-        self.x_bprop = engine.compile(bundle.programs["bprop"])
         self._h = ctypes.c_void_p()
-        check(_native.lib().trx_objective_create(self.x_prog._h, self.x_prep._h, self.x_bprop._h, lanes,
-                                                 max_device_bytes, engine.device, ctypes.byref(self._h)))
+        blobs = [bundle.programs[n] for n in ("prog", "prep", "bprop")]
+        bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
+        check(_native.lib().trx_objective_create(bufs[0], len(blobs[0]), bufs[1], len(blobs[1]), bufs[2], len(blobs[2]),
+                                                 lanes, max_device_bytes, engine.device, 1 if fused else 0,
+                                                 ctypes.byref(self._h)))
         self.lanes = lanes
         self.n_x = self.info("n_x")
         self._g = np.empty(self.n_x)

@@ -15,6 +15,7 @@
 
 #include "../../include/trx_b200.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_lower.h"
+#include "../../robio_2021_dexopt_b200/csrc/trx_fuse.h"
 #include "../../robio_2021_dexopt_b200/csrc/vm_exec.cuh"
 
 namespace {
@@ -68,6 +69,30 @@ int emu_program_create_from_blob(const void *blob, size_t bytes, int warps, emu_
     return fail(m.find("unsupported operator") != std::string::npos ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, m);
   }
 }
+// the objective's fused lowering (csrc/trx_fuse.h): forward+prepare and adjoint
+int emu_fused_create(const void *prog, size_t prog_n, const void *prep, size_t prep_n, const void *bprop, size_t bprop_n,
+                     int warps, int ring_slots, int sync_penalty, emu_program **fwd, emu_program **adj) {
+  *fwd = *adj = nullptr;
+  try {
+    trxfile::Program p_prog, p_prep, p_bprop;
+    trxfile::decodeProgram(prog, prog_n, p_prog);
+    trxfile::decodeProgram(prep, prep_n, p_prep);
+    trxfile::decodeProgram(bprop, bprop_n, p_bprop);
+    std::unique_ptr<emu_program> f(new emu_program()), a(new emu_program());
+    trx::FuseOptions opt;
+    opt.n_warps = (uint32_t)warps;
+    opt.ring_slots = (uint32_t)ring_slots;
+    opt.sync_penalty = (uint32_t)sync_penalty;
+    trx::lowerObjective(p_prog, p_prep, p_bprop, opt, f->low, a->low);
+    f->scalar_inputs = f->scalar_outputs = TRX_SCALAR_SHARED;
+    a->scalar_inputs = a->scalar_outputs = TRX_SCALAR_REDUCE;
+    *fwd = f.release();
+    *adj = a.release();
+    return TRX_OK;
+  } catch (const std::exception &e) {
+    return fail(TRX_ERR_INVALID, e.what());
+  }
+}
 void emu_program_destroy(emu_program *p) { delete p; }
 int emu_program_buffer_bytes(const emu_program *p, int which, uint64_t lanes, uint64_t *bytes) {
   *bytes = p->layout(which).wideElems(lanes) * 8;
@@ -82,6 +107,11 @@ int emu_program_stat(const emu_program *p, const char *key, uint64_t *value) {
   else if (k == "memory_size") *value = p->low.memory_size;
   else if (k == "max_level_width") *value = p->low.max_level_width;
   else if (k == "arg_bytes_per_tile") *value = p->low.arg_bytes_per_tile;
+  else if (k == "n_ring_reads") *value = p->low.n_ring_reads;
+  else if (k == "n_image_reads") *value = p->low.n_image_reads;
+  else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;
+  else if (k == "n_dual_writes") *value = p->low.n_dual_writes;
+  else if (k == "n_image_writes") *value = p->low.n_image_writes;
   else return fail(TRX_ERR_INVALID, "unknown statistic");
   return TRX_OK;
 }
@@ -148,6 +178,7 @@ int emu_execute(const emu_program *p, emu_memory *m) {
     double *mem = m->mem.data() + t * m->tile_stride;
     for (size_t i = 0; i < low.const_idx.size(); i++) std::memcpy(mem + low.const_idx[i], &low.const_bits[i], 8);
     uint32_t W = low.n_warps;
+    std::vector<double> rings((size_t)W * std::max<uint32_t>(low.ring_doubles, 1), 0.0);
     std::vector<const uint32_t *> pc(W);
     for (uint32_t w = 0; w < W; w++) pc[w] = low.stream.data() + low.stream_begin[w];
     bool done = false;
@@ -174,9 +205,13 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             pc[w] += 1 + nargs + 2;
             continue;
           }
+          bool dual = (hdr >> 22) & 1u;
           for (int lane32 = 0; lane32 < 32; lane32++) {
             trxvm::Ctx c;
             c.m = mem;
+            c.ring = rings.data() + (size_t)w * low.ring_doubles;
+            c.nargs = nargs;
+            c.dual = dual;
             int sub;
             if (wide) {
               sub = lane32;
@@ -192,7 +227,7 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             c.a = pc[w] + 1 + sub;
             if (sub < nsub) trxvm::exec(op, c);
           }
-          pc[w] += 1 + nargs * (wide ? 32 : 4);
+          pc[w] += 1 + (dual ? 2 * nargs : nargs) * (wide ? 32 : 4);
         }
       }
     }

@@ -99,7 +99,21 @@ class EmuEngine:
         for n in ("emu_input", "emu_parameterize", "emu_output"):
             getattr(self.lib, n).argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64]
         self.lib.emu_execute.argtypes = [c.c_void_p, c.c_void_p]
+        self.lib.emu_fused_create.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t,
+                                              c.c_int, c.c_int, c.c_int, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p)]
         self.warps = warps
+
+    def compile_fused(self, bundle, ring_slots=192, sync_penalty=900):
+        """(forward+prepare, adjoint) executables from the objective's fused lowering"""
+        blobs = [bundle.programs[n] for n in ("prog", "prep", "bprop")]
+        bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
+        fwd, adj = EmuExecutable(self.lib, self.warps), EmuExecutable(self.lib, self.warps)
+        st = self.lib.emu_fused_create(bufs[0], len(blobs[0]), bufs[1], len(blobs[1]), bufs[2], len(blobs[2]),
+                                       self.warps, ring_slots, sync_penalty, ctypes.byref(fwd._h), ctypes.byref(adj._h))
+        if st != 0:
+            raise RuntimeError("emu status %d: %s" % (st, self.lib.emu_last_error().decode()))
+        fwd._compiled = adj._compiled = True
+        return fwd, adj
 
     def createMemory(self, lanes=8):
         return EmuMemory(self.lib, lanes)

@@ -49,3 +49,37 @@ def test_gradient_descent_iterates(emu_engine, golden, fixture):
         return loss, state["x"]
 
     parity.check_gd_iterates(step, bundle)
+
+
+def _fused_objective(emu_engine, bundle, ref, ring_slots=192, sync_penalty=900):
+    from robio_2021_dexopt_b200 import trxfile
+    fwd, adj = emu_engine.compile_fused(bundle, ring_slots, sync_penalty)
+    prog = bundle.view("prog")
+    params = parity.tile_arrays(ref, "params")
+    mem = emu_engine.createMemory(8 * len(params))
+    if prog.parameters:
+        fwd.parameterize(trxfile.tiles_to_wide(prog.parameters, params), mem)
+    r = fwd.run(ref.arrays["x"], mem)
+    parity.assert_close(r, trxfile.tiles_to_wide(prog.outputs, parity.tile_arrays(ref, "r")), "residuals")
+    g = adj.run(r, mem)
+    parity.assert_close(g, ref.arrays["g_total"], "gradient")
+    return fwd, adj
+
+
+@pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
+@pytest.mark.parametrize("ring_slots,sync_penalty", [(192, 900), (16, 100), (192, 0)])
+def test_fused_lowering_of_reference_tapes(emu_engine, golden, fixture, ring_slots, sync_penalty):
+    """the objective's latency-oriented lowering (chain scheduling, per-warp slot rings, write-through
+    only where needed; csrc/trx_fuse.h) on tapes recorded by the reference"""
+    ref = golden(fixture)
+    fwd, adj = _fused_objective(emu_engine, ref, ref, ring_slots, sync_penalty)
+    assert fwd.stat("n_ring_reads") > 0 and adj.stat("n_ring_reads") > 0
+
+
+@pytest.mark.parametrize("fuse_dense", [0, 1])
+def test_fused_lowering_of_product_tapes(emu_engine, golden, fuse_dense):
+    import robio_2021_dexopt_b200 as pkg
+    ref = golden("dexsyn_dropout_outer2.trxb.xz")
+    mine = pkg.build_dexsyn(frames=2, hidden=4, extra_fixed=2, dropout=1, outer=2, fuse_dense=fuse_dense)
+    fwd, adj = _fused_objective(emu_engine, mine, ref)
+    assert fwd.stat("n_ring_only_writes") > 0  # some results never leave the chip
