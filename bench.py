@@ -31,7 +31,7 @@ LANES_PER_GPU = int(os.environ.get("BENCH_LANES", 1024))
 KIND = os.environ.get("BENCH_KIND", "handarm")
 HIDDEN = int(os.environ.get("BENCH_HIDDEN", 64))
 FUSE_DENSE = int(os.environ.get("BENCH_FUSE_DENSE", 1))
-FUSED = int(os.environ.get("BENCH_FUSED", 1))
+FUSED = int(os.environ.get("BENCH_FUSED", 0))
 MAX_DEVICE_BYTES = int(float(os.environ.get("BENCH_MAX_DEVICE_GB", 150)) * 1e9)
 CPU_SAMPLE_FRAMES = int(os.environ.get("BENCH_CPU_FRAMES", 16))
 CPU_SAMPLE_SECONDS = float(os.environ.get("BENCH_CPU_SECONDS", 12))

@@ -155,6 +155,7 @@ inline void hostExec(const trxfile::Program &p, const DecodedInst &in,
     c.ring = nullptr;
     c.nargs = (int)in.n_args;
     c.dual = false;
+    c.rings = false;
     c.a = args;
     c.as = 1;
     c.cs = (lw == 1) ? 1 : 8;

@@ -46,7 +46,8 @@ trx_status fail(trx_status code, const std::string &msg) {
 
 // The interpreter.  grid = tiles, block = W warps; dynamic shared memory = W slot rings.
 // record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21] | dual[22]
-template <int kMaxWarps>
+// kRings = false: generic executables (every slot in the memory image, plain global loads/stores).
+template <int kMaxWarps, bool kRings>
 __global__ void __launch_bounds__(kMaxWarps * 32)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
                   uint64_t tile_stride, uint32_t ring_doubles) {
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
   trxvm::Ctx c;
   c.m = m;
   c.ring = trx_rings + (size_t)warp * ring_doubles;
+  c.rings = kRings;
+  c.dual = false;
   while (true) {
     const uint32_t op = hdr & 0x7ffu;
     if (op == trx::OP_END) break;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       pc = next;
       continue;
     }
-    c.dual = (hdr >> 22) & 1u;
+    if (kRings) c.dual = (hdr >> 22) & 1u;
     c.nargs = nargs;
     int sub;
     if (wide) {
@@ -96,10 +99,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
     c.a = pc + 1 + sub;
     const uint32_t *next = pc + 1 + (c.dual ? 2 * nargs : nargs) * c.as;
     hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
-    // pull the lines of the following record(s) towards L1 while this one executes
-    if (lane32 < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
+    if (kRings) {
+      // pull the lines of the following record(s) towards L1 while this one executes
+      if (lane32 < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
+    }
     if (sub < nsub) trxvm::exec(op, c);
-    __syncwarp();  // ring slots written by one quarter-warp may be read by another in the next record
+    if (kRings) __syncwarp();  // ring slots written by one quarter-warp may be read by another in the next record
     pc = next;
   }
 }
@@ -553,13 +558,18 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
   if (p->low.n_instructions) {
     uint32_t W = p->low.n_warps;
     size_t smem = (size_t)W * p->low.ring_doubles * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
+    if (p->low.ring_doubles) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+      }
+      trx_vm_kernel<16, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                            m->tile_stride, p->low.ring_doubles);
+    } else {
+      trx_vm_kernel<16, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                          m->tile_stride, 0);
     }
-    trx_vm_kernel<16><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                   m->tile_stride, p->low.ring_doubles);
     g_launches++;
   }
   TRX_CUDA(cudaGetLastError());

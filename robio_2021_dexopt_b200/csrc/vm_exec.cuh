@@ -30,14 +30,18 @@ struct Ctx {
   int lo;              // lane offset (0..7)
   int nargs;           // number of arguments (rows) of the record
   bool dual;           // record has a second row of words per argument
+  bool rings;          // false: every argument word is a memory-image slot (generic executables)
 };
 
 TRX_HD uint32_t argword(const Ctx &c, int k) { return c.a[k * c.as]; }
-TRX_HD double *slotptr(const Ctx &c, uint32_t w) { return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w); }
+TRX_HD double *slotptr(const Ctx &c, uint32_t w) {
+  if (!c.rings) return c.m + w;
+  return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w);
+}
 TRX_HD double ld(const Ctx &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.cs + c.lo]; }
 TRX_HD void st(const Ctx &c, int k, int j, double v) {
   slotptr(c, argword(c, k))[j * c.cs + c.lo] = v;
-  if (c.dual) {
+  if (c.rings && c.dual) {
     uint32_t w2 = c.a[(c.nargs + k) * c.as];
     if (w2 != kNoSlot) c.m[w2 + j * c.cs + c.lo] = v;
   }

@@ -212,6 +212,7 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             c.ring = rings.data() + (size_t)w * low.ring_doubles;
             c.nargs = nargs;
             c.dual = dual;
+            c.rings = true;
             int sub;
             if (wide) {
               sub = lane32;
