@@ -178,7 +178,8 @@ def main():
     t_build = time.time()
     bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop", fuse_dense=FUSE_DENSE)
     engine = pkg.CudaEngine(local_rank)
-    obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES, fused=bool(FUSED))
+    obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES, fused=bool(FUSED),
+                        scalar_rows=(rank == 0))
     t_build = time.time() - t_build
     n_x = obj.n_x
     prog = bundle.view("prog")

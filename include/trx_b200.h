@@ -178,7 +178,12 @@ typedef struct trx_objective trx_objective;
 /* flags: TRX_OBJECTIVE_FUSED lowers forward+prepare and the adjoint with chain scheduling and on-chip
  * slot rings (csrc/trx_fuse.h) instead of as three generic executables.  The three programs are given
  * as TRXB program payloads (include/trx_file.h); the objective owns everything it builds from them. */
-enum { TRX_OBJECTIVE_FUSED = 1 };
+enum {
+  TRX_OBJECTIVE_FUSED = 1,
+  /* multi-GPU sharding: lane-independent (scalar-typed) residual rows are identical on every rank and must
+   * count once over the job; every rank except one sets this flag */
+  TRX_OBJECTIVE_NO_SCALAR_ROWS = 2
+};
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
                                 int device, int flags, trx_objective **out);

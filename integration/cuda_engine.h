@@ -1,0 +1,164 @@
+// cuda_engine.h -- tractor::Engine implementation backed by the B200 tape engine.
+//
+// This is the reference-side binding a tractor maintainer adds to switch dexopt from
+//     auto engine = std::make_shared<tractor::SimpleEngine>();          (dexopt/src/dexopt.cpp:78)
+// to
+//     auto engine = std::make_shared<tractor::CudaEngine>();
+// It derives from the reference's own interface (tractor/include/tractor/core/engine.h:11-112) and
+// forwards the five private virtuals of Executable to the C ABI in include/trx_b200.h:
+//     _compile       -> trx_program_create   (Program -> neutral description: Operator::name() + argument
+//                                              layouts from Operator::arguments(), ports, constants)
+//     _execute       -> trx_execute
+//     _input         -> trx_input
+//     _output        -> trx_output
+//     _parameterize  -> trx_parameterize
+// Errors of the C ABI are rethrown as std::runtime_error, the reference's error channel
+// (core/engine.h:20-24, src/core/engine.cpp:44-48).
+//
+// Needs the tractor headers, so it is compiled only where the reference is available
+// (oracle/ref_build/ref_cuda_engine_test.cpp builds and runs it against SimpleEngine).
+#pragma once
+#include <cxxabi.h>
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <tractor/core/engine.h>
+#include <tractor/core/operator.h>
+#include <tractor/core/program.h>
+
+#include "../include/trx_b200.h"
+
+namespace tractor {
+
+class CudaEngine : public Engine {
+  int _device = 0;
+  uint64_t _lanes = 8;  // rollouts per Memory; 8 = one Batch<double,8> image, byte-compatible buffers
+
+  static void check(trx_status s) {
+    if (s != TRX_OK) throw std::runtime_error(std::string("CudaEngine: ") + trx_last_error());
+  }
+
+  static void classify(const TypeInfo &t, uint8_t &lanes, uint8_t &elem) {
+    int status = 0;
+    char *d = abi::__cxa_demangle(t.name(), nullptr, nullptr, &status);
+    std::string n = (status == 0 && d) ? d : t.name();
+    free(d);
+    lanes = 1;
+    elem = 0;
+    auto pos = n.find("tractor::Batch<");
+    if (pos != std::string::npos) lanes = (uint8_t)std::atoi(n.c_str() + n.find(',', pos) + 1);
+    else if (n.find("unsigned long") != std::string::npos) elem = 1;
+  }
+
+  class MemoryImpl : public Memory {
+   public:
+    trx_memory *handle = nullptr;
+    MemoryImpl(uint64_t lanes, int device) { check(trx_memory_create(lanes, device, &handle)); }
+    ~MemoryImpl() override { trx_memory_destroy(handle); }
+    MemoryImpl(const MemoryImpl &) = delete;
+    MemoryImpl &operator=(const MemoryImpl &) = delete;
+  };
+
+  class ExecutableImpl : public Executable {
+    int _device;
+    trx_program *_program = nullptr;
+
+    template <class Ports> static std::vector<trx_port_desc> ports(const Ports &src) {
+      std::vector<trx_port_desc> out;
+      for (auto &p : src) {
+        trx_port_desc d{};
+        d.address = p.address();
+        d.offset = p.offset();
+        d.size = (uint32_t)p.size();
+        classify(p.typeInfo(), d.lanes, d.elem);
+        out.push_back(d);
+      }
+      return out;
+    }
+    static trx_memory *mem(const std::shared_ptr<Memory> &m) { return static_cast<MemoryImpl *>(m.get())->handle; }
+
+   protected:
+    void _compile(const Program &program) override {
+      std::vector<const Operator *> op_list;
+      std::vector<std::vector<trx_arg_desc>> arg_store;
+      std::vector<uint64_t> code;
+      uint64_t n_inst = 0;
+      for (auto &inst : program.instructions()) {
+        const Operator *op = inst.op();
+        size_t index = 0;
+        while (index < op_list.size() && op_list[index] != op) index++;
+        if (index == op_list.size()) {
+          op_list.push_back(op);
+          std::vector<trx_arg_desc> args;
+          for (auto &a : op->arguments()) {
+            trx_arg_desc d{};
+            d.size = (uint32_t)a.size();
+            d.is_input = a.isInput() ? 1 : 0;
+            classify(a.typeInfo(), d.lanes, d.elem);
+            args.push_back(d);
+          }
+          arg_store.push_back(std::move(args));
+        }
+        code.push_back(index);
+        for (auto a : inst.args()) code.push_back((uint64_t)a);
+        n_inst++;
+      }
+      std::vector<trx_op_desc> ops(op_list.size());
+      for (size_t i = 0; i < ops.size(); i++) {
+        ops[i].name = op_list[i]->name().c_str();
+        ops[i].n_args = (uint32_t)arg_store[i].size();
+        ops[i].args = arg_store[i].data();
+      }
+      auto in = ports(program.inputs()), par = ports(program.parameters()), out = ports(program.outputs()),
+           con = ports(program.constants());
+      trx_program_desc d{};
+      d.memory_size = program.memorySize();
+      d.n_ops = (uint32_t)ops.size();
+      d.ops = ops.data();
+      d.n_instructions = n_inst;
+      d.n_code_words = code.size();
+      d.code = code.data();
+      d.n_inputs = (uint32_t)in.size();
+      d.inputs = in.data();
+      d.n_parameters = (uint32_t)par.size();
+      d.parameters = par.data();
+      d.n_outputs = (uint32_t)out.size();
+      d.outputs = out.data();
+      d.n_constants = (uint32_t)con.size();
+      d.constants = con.data();
+      d.n_const_data = program.constData().size();
+      d.const_data = program.constData().data();
+      if (_program) trx_program_destroy(_program);
+      _program = nullptr;
+      check(trx_program_create(&d, _device, &_program));
+    }
+    void _execute(const std::shared_ptr<Memory> &memory) const override { check(trx_execute(_program, mem(memory), nullptr)); }
+    void _input(const Buffer &input, const std::shared_ptr<Memory> &memory) const override {
+      check(trx_input(_program, mem(memory), input.data(), input.size(), nullptr));
+    }
+    void _parameterize(const Buffer &data, const std::shared_ptr<Memory> &memory) const override {
+      check(trx_parameterize(_program, mem(memory), data.data(), data.size(), nullptr));
+    }
+    void _output(const std::shared_ptr<const Memory> &memory, Buffer &output) const override {
+      output.resize(outputBufferSize());
+      auto *m = static_cast<const MemoryImpl *>(memory.get())->handle;
+      check(trx_output(_program, m, output.data(), output.size(), nullptr));
+    }
+
+   public:
+    explicit ExecutableImpl(int device) : _device(device) {}
+    ~ExecutableImpl() override { trx_program_destroy(_program); }
+  };
+
+ public:
+  explicit CudaEngine(int device = 0) : _device(device) {
+    if (trx_device_count() <= 0) throw std::runtime_error("CudaEngine: no CUDA device (there is no CPU fallback)");
+  }
+  std::shared_ptr<Memory> createMemory() override { return std::make_shared<MemoryImpl>(_lanes, _device); }
+  std::shared_ptr<Executable> createExecutable() override { return std::make_shared<ExecutableImpl>(_device); }
+};
+
+}  // namespace tractor

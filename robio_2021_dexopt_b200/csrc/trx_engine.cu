@@ -636,6 +636,7 @@ struct trx_objective {
   // otherwise the three programs lowered one by one as generic executables (trx_lower.h)
   trx_program *prog = nullptr, *prep = nullptr, *bprop = nullptr;
   bool fused = false;
+  bool scalar_rows = true;  // false: lane-independent residual rows are another rank's to count
   int device = 0;
   uint64_t lanes = 0, chunk_lanes = 0, n_chunks = 0;
   uint64_t n_x = 0;
@@ -682,6 +683,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
   if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
   std::unique_ptr<trx_objective> o(new trx_objective());
   o->fused = (flags & TRX_OBJECTIVE_FUSED) != 0;
+  o->scalar_rows = (flags & TRX_OBJECTIVE_NO_SCALAR_ROWS) == 0;
   {
     trxfile::Program p_prog, p_prep, p_bprop;
     try {
@@ -842,7 +844,7 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
     if ((s = trx_execute(o->prog, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[1], stream);
     trx_seed_kernel<<<(unsigned)chunk_tiles, 256, 0, stream>>>(o->d_seed, o->n_seed, m->d_mem, m->tile_stride,
-                                                              c == 0 ? 1 : 0, o->d_partial + c * chunk_tiles);
+                                                              (c == 0 && o->scalar_rows) ? 1 : 0, o->d_partial + c * chunk_tiles);
     g_launches++;
     if (o->prep && (s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[2], stream);

@@ -24,15 +24,17 @@ class Objective:
     """objective + gradient over R rollouts of a recorded problem (prog/prep/bprop of one bundle)"""
 
     def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0,
-                 fused: bool = True):
+                 fused: bool = True, scalar_rows: bool = True):
         """fused=True: forward+prepare and adjoint lowered with chain scheduling and on-chip slot rings
-        (csrc/trx_fuse.h); fused=False: the three programs as generic executables (csrc/trx_lower.h)"""
+        (csrc/trx_fuse.h); fused=False: the three programs as generic executables (csrc/trx_lower.h).
+        scalar_rows=False: this rank does not count the lane-independent residual rows (multi-GPU)"""
         self.engine = engine
         self._h = ctypes.c_void_p()
         blobs = [bundle.programs[n] for n in ("prog", "prep", "bprop")]
         bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
         check(_native.lib().trx_objective_create(bufs[0], len(blobs[0]), bufs[1], len(blobs[1]), bufs[2], len(blobs[2]),
-                                                 lanes, max_device_bytes, engine.device, 1 if fused else 0,
+                                                 lanes, max_device_bytes, engine.device,
+                                                 (1 if fused else 0) | (0 if scalar_rows else 2),
                                                  ctypes.byref(self._h)))
         self.lanes = lanes
         self.n_x = self.info("n_x")

@@ -206,3 +206,55 @@ def test_fused_dense_gd_iterates(cuda_engine, golden, fixture, options):
     solver = pkg.GradientDescentSolver(obj, learning_rate=float(ref.arrays["gd/learning_rate"][0]))
     solver.gather(ref.arrays["x"])
     parity.check_gd_iterates(lambda: (solver.step(), solver.scatter()), ref)
+
+
+@pytest.mark.gpu
+def test_reference_code_runs_on_cuda_engine_through_the_tractor_interface():
+    """drop-in boundary: reference recording + buildGradients + Executable::run driven through
+    tractor::SimpleEngine and through tractor::CudaEngine (integration/cuda_engine.h), compared inside
+    the binary oracle/_ref/ref_cuda_engine_test (built from oracle/ref_build where the reference exists)"""
+    import json
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cuda_engine_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_cuda_engine_test is not built (needs the reference sources)")
+    out = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["err_r"] < 1e-9 and res["err_g"] < 1e-9 and res["err_h"] < 1e-9
+    assert res["residuals"] > 1000
+
+
+@pytest.mark.gpu
+def test_cuda_engine_against_the_oracle_restatement_on_fresh_inputs(cuda_engine, golden):
+    """seeded random policy parameters and lane parameters that are in no fixture: CUDA engine vs the
+    numpy restatement of the reference interpreter (oracle/tape_oracle.py)"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tape_oracle as oracle
+    from robio_2021_dexopt_b200 import trxfile
+    bundle = golden("dexsyn_small.trxb.xz")
+    prog = bundle.view("prog")
+    rng = np.random.default_rng(123)
+    x = 0.2 * rng.standard_normal(bundle.arrays["x"].size)
+    tiles = 3
+    params = [np.concatenate([rng.uniform(-0.01, 0.01, 16), rng.uniform(0, 6.28, 8)]) for _ in range(tiles)]
+    xs = {n: oracle.OracleExecutable(bundle.view(n)) for n in ("prog", "prep", "bprop")}
+    scalar = np.concatenate([np.full(p.size // 8, p.lanes == 1) for p in prog.outputs])
+    r_tiles, g_want, loss_want = [], 0.0, 0.0
+    for t in range(tiles):
+        mem = oracle.OracleMemory()
+        xs["prog"].parameterize(params[t], mem)
+        r = xs["prog"].run(x, mem)
+        r_tiles.append(r)
+        rr = np.where(scalar, 0.0, r) if t else r
+        loss_want += float(rr @ rr)
+        xs["prep"].execute(mem)
+        g_want = g_want + xs["bprop"].run(rr, mem)
+    import robio_2021_dexopt_b200 as pkg
+    for fused in (False, True):
+        obj = pkg.Objective(cuda_engine, bundle, lanes=8 * tiles, fused=fused)
+        obj.parameterize(trxfile.tiles_to_wide(prog.parameters, params))
+        loss, g = obj.evaluate(x)
+        assert abs(loss - loss_want) <= 1e-10 * abs(loss_want)
+        parity.assert_close(g, g_want, "gradient (fused=%s)" % fused, rtol=1e-9)
