@@ -74,6 +74,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
     const bool wide = (hdr >> 11) & 1u;
     const int nsub = (int)((hdr >> 12) & 31u) + 1;
     const int nargs = (int)((hdr >> 17) & 15u);
+    if (op == trx::OP_PREFETCH) {
+      // software prefetch record: one 128-byte line of the tile image per lane, into L2
+      const uint32_t *next = pc + 33;
+      hdr = __ldg(next);
+      if (lane32 < nsub) {
+        const double *line = m + (size_t)__ldg(pc + 1 + lane32) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+      }
+      pc = next;
+      continue;
+    }
     if ((hdr >> 21) & 1u) {
       // block-cooperative record: every warp holds it at the same stream position
       const uint32_t *next = pc + 1 + nargs + 2;
@@ -364,6 +375,7 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
   try {
     trx::LowerOptions opt;
     if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_PREFETCH")) opt.prefetch_distance = (uint32_t)atoi(w);
     trx::lowerProgram(src, opt, p->low);
   } catch (const std::exception &e) {
     std::string msg = e.what();
@@ -475,6 +487,7 @@ trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *val
   else if (k == "max_level_width") *value = p->low.max_level_width;
   else if (k == "n_constants") *value = p->low.const_idx.size();
   else if (k == "ring_doubles") *value = p->low.ring_doubles;
+  else if (k == "n_prefetch_lines") *value = p->low.n_prefetch_lines;
   else if (k == "n_ring_reads") *value = p->low.n_ring_reads;
   else if (k == "n_image_reads") *value = p->low.n_image_reads;
   else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;

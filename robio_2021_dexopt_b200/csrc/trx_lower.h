@@ -82,6 +82,9 @@ inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32
 
 struct LowerOptions {
   uint32_t n_warps = 16;
+  // software prefetch: operands of level L+D that already exist are pulled into L2 while level L runs
+  // (the schedule is static, so the addresses are known); 0 = off
+  uint32_t prefetch_distance = 2;
 };
 
 struct LoweredProgram {
@@ -94,6 +97,7 @@ struct LoweredProgram {
   uint64_t arg_bytes_per_tile = 0;
   uint64_t max_level_width = 0;
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
+  uint64_t n_prefetch_lines = 0;
   uint64_t n_ring_reads = 0, n_image_reads = 0, n_ring_only_writes = 0, n_dual_writes = 0, n_image_writes = 0;
   bool has_forward = false, has_reverse = false;
   PortLayout inputs, parameters, outputs;
@@ -202,17 +206,23 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   };
   std::vector<uint32_t> wlevel(addrs.size(), 0), rlevel(addrs.size(), 0);
   uint32_t n_levels = 0;
+  // level of the last writer of each (non-block) input argument at the time it is read: decides
+  // whether the operand already exists when a prefetch for it could be issued
+  std::vector<uint32_t> arg_wlevel(src.code.size(), 0);
   for (auto &in : insts) {
     const OpSig &sig = table[ops[in.op].opcode];
     size_t na = sig.args.size();
     uint32_t lvl = 0;
     for (size_t k = 0; k < na; k++) {
       bool is_in = sig.args[k].is_input;
+      uint32_t wl = 0;
       forEachKey(in, k, [&](uint64_t key) {
         size_t id = slotId(key);
+        wl = std::max(wl, wlevel[id]);
         if (is_in) lvl = std::max(lvl, wlevel[id]);
         else lvl = std::max(lvl, std::max(wlevel[id], rlevel[id]));
       });
+      arg_wlevel[in.code_at + k] = wl;
       out.arg_bytes_per_tile += src.ops[in.op].args[k].size;
     }
     in.level = lvl + 1;
@@ -244,6 +254,43 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   }
   const uint32_t W = opt.n_warps;
   std::vector<std::vector<uint32_t>> streams(W);
+  // 128-byte lines (index = byte address / 128) that level L reads and that exist `prefetch_distance`
+  // levels earlier
+  const uint32_t PD = opt.prefetch_distance;
+  std::vector<std::vector<uint32_t>> level_lines(PD ? n_levels + 2 : 0);
+  if (PD)
+    for (auto &in : insts) {
+      const OpSig &sig = table[ops[in.op].opcode];
+      if (sig.coop) continue;
+      // the prefetch for level L is issued when level P = max(1, L - PD) starts; the operand must be
+      // complete by then (writer level < P; 0 = not written by this program: constants, ports, state of
+      // an earlier program)
+      const uint32_t P = in.level > PD ? in.level - PD : 1;
+      for (size_t k = 0; k < sig.args.size(); k++) {
+        if (!sig.args[k].is_input) continue;
+        if (arg_wlevel[in.code_at + k] >= P) continue;
+        uint64_t a = src.code[in.code_at + k], e = a + src.ops[in.op].args[k].size - 1;
+        for (uint64_t line = a / 128; line <= e / 128; line++) level_lines[in.level].push_back((uint32_t)line);
+      }
+    }
+  auto emitPrefetch = [&](uint32_t for_level) {
+    if (!PD || for_level > n_levels) return;
+    auto &lines = level_lines[for_level];
+    if (lines.empty()) return;
+    std::sort(lines.begin(), lines.end());
+    lines.erase(std::unique(lines.begin(), lines.end()), lines.end());
+    uint32_t w = 0;
+    for (size_t i = 0; i < lines.size(); i += 32) {
+      uint32_t n = (uint32_t)std::min<size_t>(32, lines.size() - i);
+      auto &s = streams[w];
+      s.push_back(HeaderBits::make(OP_PREFETCH, true, n, 0));
+      for (uint32_t j = 0; j < 32; j++) s.push_back(lines[i + (j < n ? j : 0)]);
+      w = (w + 1) % W;
+      out.n_prefetch_lines += n;
+    }
+    std::vector<uint32_t>().swap(lines);
+  };
+  for (uint32_t l = 1; l <= PD && l <= n_levels; l++) emitPrefetch(l);  // nothing runs before level 1: warm up
   struct Bundle {
     uint16_t opcode;
     bool wide;
@@ -254,6 +301,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   std::vector<Bundle> bundles;
   std::vector<uint64_t> load(W);
   for (uint32_t level = 1; level <= n_levels; level++) {
+    emitPrefetch(level + PD);
     lvl_insts.assign(order.begin() + level_count[level], order.begin() + level_count[level + 1]);
     out.max_level_width = std::max<uint64_t>(out.max_level_width, lvl_insts.size());
     std::stable_sort(lvl_insts.begin(), lvl_insts.end(), [&](uint32_t a, uint32_t b) {

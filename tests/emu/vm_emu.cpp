@@ -195,6 +195,10 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             pc[w]++;
             break;
           }
+          if (op == trx::OP_PREFETCH) {
+            pc[w] += 33;
+            continue;
+          }
           bool wide = (hdr >> 11) & 1u;
           int nsub = (int)((hdr >> 12) & 31u) + 1;
           int nargs = (int)((hdr >> 17) & 15u);
