@@ -179,7 +179,7 @@ def main():
     bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop", fuse_dense=FUSE_DENSE)
     engine = pkg.CudaEngine(local_rank)
     obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES, fused=bool(FUSED),
-                        scalar_rows=(rank == 0))
+                        separate=bool(int(os.environ.get("BENCH_SEPARATE", 0))), scalar_rows=(rank == 0))
     t_build = time.time() - t_build
     n_x = obj.n_x
     prog = bundle.view("prog")
@@ -291,6 +291,7 @@ def main():
             "interpreted_tape_gbs": tape_bytes / (8.0 * FRAMES) * units / world / (sum(kernel_ms) / args.steps * 1e-3) / 1e9,
         },
         "loss": loss,
+        "lowering_stats": {k: {q: obj.info("%s.%s" % (k, q)) for q in ("n_instructions", "n_levels", "n_bundles", "stream_words", "n_ring_reads", "n_image_reads", "n_ring_only_writes", "n_dual_writes", "n_image_writes", "n_prefetch_lines")} for k in ("prog", "prep", "bprop")},
         "setup_s": t_build,
         "chunks": n_chunks,
         "device_bytes": obj.info("device_bytes"),

@@ -164,6 +164,9 @@ trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed
 /* number of kernels this library has launched since load (for launch accounting) */
 uint64_t trx_kernel_launch_count(void);
 
+/* development aid: per-level barrier arrival / release clocks of tile 0 (see csrc/trx_engine.cu) */
+trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer);
+
 /* debug: copy `bytes` of tile `tile`'s memory image starting at byte `address` to the host */
 trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes);
 
@@ -182,7 +185,10 @@ enum {
   TRX_OBJECTIVE_FUSED = 1,
   /* multi-GPU sharding: lane-independent (scalar-typed) residual rows are identical on every rank and must
    * count once over the job; every rank except one sets this flag */
-  TRX_OBJECTIVE_NO_SCALAR_ROWS = 2
+  TRX_OBJECTIVE_NO_SCALAR_ROWS = 2,
+  /* lower x_prog, x_prep, x_bprop as three separate executables (default: x_prep is interleaved into
+   * x_prog and the two sweeps are two launches) */
+  TRX_OBJECTIVE_SEPARATE = 4
 };
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,

@@ -156,6 +156,7 @@ inline void hostExec(const trxfile::Program &p, const DecodedInst &in,
     c.nargs = (int)in.n_args;
     c.dual = false;
     c.rings = false;
+    c.preloaded = false;
     c.a = args;
     c.as = 1;
     c.cs = (lw == 1) ? 1 : 8;

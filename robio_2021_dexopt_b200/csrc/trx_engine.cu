@@ -27,6 +27,7 @@
 
 namespace {
 
+long long *g_trace = nullptr;  // development aid (trx_debug_trace)
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -47,11 +48,12 @@ trx_status fail(trx_status code, const std::string &msg) {
 // The interpreter.  grid = tiles, block = W warps; dynamic shared memory = W slot rings.
 // record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21] | dual[22]
 // kRings = false: generic executables (every slot in the memory image, plain global loads/stores).
-template <int kMaxWarps, bool kRings>
-__global__ void __launch_bounds__(kMaxWarps * 32)
+template <int kMaxWarps, bool kRings, bool kStreamPrefetch>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
-                  uint64_t tile_stride, uint32_t ring_doubles) {
+                  uint64_t tile_stride, uint32_t ring_doubles, long long *trace) {
   extern __shared__ double trx_rings[];
+  uint32_t trace_level = 0;
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
   const int lane32 = threadIdx.x & 31;
@@ -62,12 +64,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
   c.ring = trx_rings + (size_t)warp * ring_doubles;
   c.rings = kRings;
   c.dual = false;
+  c.preloaded = false;
   while (true) {
     const uint32_t op = hdr & 0x7ffu;
     if (op == trx::OP_END) break;
     if (op == trx::OP_BARRIER) {
       pc += 1;
       hdr = __ldg(pc);
+      if (trace && blockIdx.x == 0) {  // development aid: arrival / release clocks per level
+        long long t0 = clock64();
+        int arrived = __syncthreads_count(1);  // returns a value: the clock read below cannot issue before release
+        long long t1;
+        asm volatile("{ .reg .u32 d; add.u32 d, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(t1) : "r"(arrived));
+        if (lane32 == 0) {
+          trace[((size_t)trace_level * (blockDim.x / 32) + warp) * 2] = t0;
+          trace[((size_t)trace_level * (blockDim.x / 32) + warp) * 2 + 1] = t1;
+        }
+        trace_level++;
+        continue;
+      }
       __syncthreads();
       continue;
     }
@@ -108,14 +123,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       c.lo = lane32 & 7;
     }
     c.a = pc + 1 + sub;
+    if (!kRings) trxvm::preload_args(c);
     const uint32_t *next = pc + 1 + (c.dual ? 2 * nargs : nargs) * c.as;
     hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
-    if (kRings) {
-      // pull the lines of the following record(s) towards L1 while this one executes
-      if (lane32 < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
+    // the stream is read sequentially: pull the following lines towards L1 (and further ones into L2)
+    // while this record executes
+    if (kStreamPrefetch) {
+      if (lane32 < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
+      else if (lane32 < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(next + 256 + 64 * (lane32 - 4)));
     }
     if (sub < nsub) trxvm::exec(op, c);
-    if (kRings) __syncwarp();  // ring slots written by one quarter-warp may be read by another in the next record
+    __syncwarp();  // chain-scheduled streams: the next record of this warp may read what this one wrote
     pc = next;
   }
 }
@@ -362,6 +380,19 @@ const char *trx_op_signature(int i) {
 
 uint64_t trx_kernel_launch_count(void) { return g_launches.load(); }
 
+// development aid: the next generic-VM launches record, for tile 0, the clock at which every warp
+// arrives at / leaves each level barrier.  n_words = capacity of the device buffer in 64-bit words.
+trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer) {
+  if (g_trace) cudaFree(g_trace);
+  g_trace = nullptr;
+  if (n_words) {
+    TRX_CUDA(cudaMalloc(&g_trace, n_words * 8));
+    TRX_CUDA(cudaMemset(g_trace, 0, n_words * 8));
+  }
+  if (device_buffer) *device_buffer = g_trace;
+  return TRX_OK;
+}
+
 // uploads p->low (already lowered) to the device
 static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int scalar_in, int scalar_out,
                                 trx_program **out);
@@ -574,14 +605,19 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
     if (p->low.ring_doubles) {
       static bool attr_set = false;
       if (!attr_set) {
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
       }
-      trx_vm_kernel<16, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                            m->tile_stride, p->low.ring_doubles);
+      trx_vm_kernel<16, true, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                            m->tile_stride, p->low.ring_doubles, nullptr);
     } else {
-      trx_vm_kernel<16, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                          m->tile_stride, 0);
+      static int sp = getenv("TRX_STREAM_PREFETCH") ? atoi(getenv("TRX_STREAM_PREFETCH")) : 1;
+      if (sp)
+        trx_vm_kernel<16, false, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                                  m->tile_stride, 0, g_trace);
+      else
+        trx_vm_kernel<16, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
+                                                                                   m->tile_stride, 0, g_trace);
     }
     g_launches++;
   }
@@ -716,11 +752,26 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       if ((s = finishProgram(adj, device, TRX_SCALAR_REDUCE, TRX_SCALAR_REDUCE, &raw)) != TRX_OK) return s;
       o->bprop = raw;
       o->prep = nullptr;
-    } else {
+    } else if (flags & TRX_OBJECTIVE_SEPARATE) {
       if ((s = createFromFile(p_prog, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
       o->prog = raw;
       if ((s = createFromFile(p_prep, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
       o->prep = raw;
+      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      o->bprop = raw;
+    } else {
+      // default: x_prep interleaved into x_prog (every prepare instruction directly after its compute
+      // instruction), level-scheduled as one program: the prepare work fills warps that the narrow
+      // forward levels leave idle, and one launch disappears
+      trxfile::Program combined;
+      try {
+        trx::combineForward(p_prog, p_prep, combined);
+      } catch (const std::exception &e) {
+        return fail(TRX_ERR_INVALID, e.what());
+      }
+      if ((s = createFromFile(combined, device, TRX_SCALAR_SHARED, TRX_SCALAR_SHARED, &raw)) != TRX_OK) return s;
+      o->prog = raw;
+      o->prep = nullptr;
       if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
       o->bprop = raw;
     }

@@ -92,6 +92,7 @@ inline void lowerFused(const trxfile::Program &src, const std::unordered_set<uin
   const uint32_t W = opt.n_warps;
   if (W < 1 || W > 16) throw std::runtime_error("n_warps out of range (1..16)");
   if (opt.ring_slots * 8 > 0xffff) throw std::runtime_error("ring too large for 16-bit offsets");
+  if (const char *e = getenv("TRX_OP_COST")) const_cast<FuseOptions &>(opt).op_base_cost = (uint32_t)atoi(e);
   if (src.memory_size / 8 >= 0x7fffffffull) throw std::runtime_error("memory image too large for 31-bit slot indices");
 
   // ---- operators

@@ -31,9 +31,18 @@ struct Ctx {
   int nargs;           // number of arguments (rows) of the record
   bool dual;           // record has a second row of words per argument
   bool rings;          // false: every argument word is a memory-image slot (generic executables)
+  bool preloaded;      // argument words were fetched into w[] when the record started
+  uint32_t w[12];      // (registers: every use indexes it with a compile-time constant)
 };
 
-TRX_HD uint32_t argword(const Ctx &c, int k) { return c.a[k * c.as]; }
+TRX_HD uint32_t argword(const Ctx &c, int k) { return c.preloaded ? c.w[k] : c.a[k * c.as]; }
+// all argument words of the record at once: independent loads, one latency instead of one per operand
+TRX_HD void preload_args(Ctx &c) {
+#pragma unroll
+  for (int k = 0; k < 12; k++)
+    if (k < c.nargs) c.w[k] = c.a[k * c.as];
+  c.preloaded = true;
+}
 TRX_HD double *slotptr(const Ctx &c, uint32_t w) {
   if (!c.rings) return c.m + w;
   return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w);

@@ -24,9 +24,10 @@ class Objective:
     """objective + gradient over R rollouts of a recorded problem (prog/prep/bprop of one bundle)"""
 
     def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0,
-                 fused: bool = True, scalar_rows: bool = True):
-        """fused=True: forward+prepare and adjoint lowered with chain scheduling and on-chip slot rings
-        (csrc/trx_fuse.h); fused=False: the three programs as generic executables (csrc/trx_lower.h).
+                 fused: bool = False, scalar_rows: bool = True, separate: bool = False):
+        """default: x_prep interleaved into x_prog, level-scheduled (csrc/trx_lower.h), two launches per chunk.
+        separate=True: prog, prep, bprop as three generic executables.  fused=True: experimental chain
+        scheduling with on-chip slot rings (csrc/trx_fuse.h).
         scalar_rows=False: this rank does not count the lane-independent residual rows (multi-GPU)"""
         self.engine = engine
         self._h = ctypes.c_void_p()
@@ -34,7 +35,7 @@ class Objective:
         bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
         check(_native.lib().trx_objective_create(bufs[0], len(blobs[0]), bufs[1], len(blobs[1]), bufs[2], len(blobs[2]),
                                                  lanes, max_device_bytes, engine.device,
-                                                 (1 if fused else 0) | (0 if scalar_rows else 2),
+                                                 (1 if fused else 0) | (0 if scalar_rows else 2) | (4 if separate else 0),
                                                  ctypes.byref(self._h)))
         self.lanes = lanes
         self.n_x = self.info("n_x")

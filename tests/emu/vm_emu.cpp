@@ -217,6 +217,7 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             c.nargs = nargs;
             c.dual = dual;
             c.rings = true;
+            c.preloaded = false;
             int sub;
             if (wide) {
               sub = lane32;

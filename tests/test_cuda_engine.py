@@ -138,15 +138,15 @@ def test_many_tiles_replicate_the_reference_tile(cuda_engine, golden):
 @pytest.mark.gpu
 @pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
 @pytest.mark.parametrize("max_bytes", [0, 1])
-@pytest.mark.parametrize("fused", [True, False])
-def test_objective_matches_reference(cuda_engine, golden, fixture, max_bytes, fused):
+@pytest.mark.parametrize("fused,separate", [(True, False), (False, False), (False, True)])
+def test_objective_matches_reference(cuda_engine, golden, fixture, max_bytes, fused, separate):
     """trx_objective_evaluate (one C-ABI call per solver step) against the reference's loss and J^T r;
     max_bytes=1 forces one lane tile per chunk, i.e. the chunked walk over rollouts"""
     import robio_2021_dexopt_b200 as pkg
     from robio_2021_dexopt_b200 import trxfile
     bundle = golden(fixture)
     prog = bundle.view("prog")
-    obj = pkg.Objective(cuda_engine, bundle, lanes=16, max_device_bytes=max_bytes, fused=fused)
+    obj = pkg.Objective(cuda_engine, bundle, lanes=16, max_device_bytes=max_bytes, fused=fused, separate=separate)
     assert obj.info("n_chunks") == (2 if max_bytes else 1)
     assert obj.info("fused") == int(fused)
     obj.parameterize(trxfile.tiles_to_wide(prog.parameters, parity.tile_arrays(bundle, "params")))
