@@ -166,6 +166,7 @@ uint64_t trx_kernel_launch_count(void);
 
 /* development aid: per-level barrier arrival / release clocks of tile 0 (see csrc/trx_engine.cu) */
 trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer);
+trx_status trx_debug_level_info(const trx_program *p, uint32_t *out, uint64_t n);
 
 /* debug: copy `bytes` of tile `tile`'s memory image starting at byte `address` to the host */
 trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes);

@@ -45,14 +45,89 @@ trx_status fail(trx_status code, const std::string &msg) {
 
 // ------------------------------------------------------------------ kernels
 
+
+// Block-cooperative dense layer on the device: operand blocks staged in shared memory, several
+// independent accumulators per thread (the host/emulation statement of the same operators is
+// trxvm::exec_coop in vm_exec.cuh).  Called by every thread of the CTA at the same stream position.
+__device__ __forceinline__ void dense_forward_dev(const uint32_t *a, double *m, double *sx) {
+  const double *x = m + a[0], *W = m + a[1], *b = m + a[2];
+  double *y = m + a[3];
+  const int n_in = (int)a[4], n_out = (int)a[5];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < n_in * 8; e += nt) sx[e] = x[e];
+  __syncthreads();
+  for (int o = tid; o < n_out * 8; o += nt) {
+    const int j = o >> 3, lane = o & 7;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int row = 0;
+#pragma unroll 2
+    for (; row + 3 < n_in; row += 4) {
+      acc0 = fma(sx[(row + 0) * 8 + lane], __ldg(W + (row + 0) * n_out + j), acc0);
+      acc1 = fma(sx[(row + 1) * 8 + lane], __ldg(W + (row + 1) * n_out + j), acc1);
+      acc2 = fma(sx[(row + 2) * 8 + lane], __ldg(W + (row + 2) * n_out + j), acc2);
+      acc3 = fma(sx[(row + 3) * 8 + lane], __ldg(W + (row + 3) * n_out + j), acc3);
+    }
+    for (; row < n_in; row++) acc0 = fma(sx[row * 8 + lane], __ldg(W + row * n_out + j), acc0);
+    y[o] = ((acc0 + acc1) + (acc2 + acc3)) + __ldg(b + j);
+  }
+  __syncthreads();  // sx is reused by the next cooperative record
+}
+
+__device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, double *sx, double *sg) {
+  const double *x = m + a[0], *W = m + a[1];
+  double *gx = m + a[4], *gW = m + a[5], *gb = m + a[6];
+  const double *gy = m + a[7];
+  const int n_in = (int)a[8], n_out = (int)a[9];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < n_in * 8; e += nt) sx[e] = x[e];
+  for (int e = tid; e < n_out * 8; e += nt) sg[e] = gy[e];
+  __syncthreads();
+  // gx[i] = sum_j gy[j] * W[i][j]
+  for (int o = tid; o < n_in * 8; o += nt) {
+    const int i = o >> 3, lane = o & 7;
+    const double *Wi = W + i * n_out;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int j = 0;
+#pragma unroll 2
+    for (; j + 3 < n_out; j += 4) {
+      acc0 = fma(sg[(j + 0) * 8 + lane], __ldg(Wi + j + 0), acc0);
+      acc1 = fma(sg[(j + 1) * 8 + lane], __ldg(Wi + j + 1), acc1);
+      acc2 = fma(sg[(j + 2) * 8 + lane], __ldg(Wi + j + 2), acc2);
+      acc3 = fma(sg[(j + 3) * 8 + lane], __ldg(Wi + j + 3), acc3);
+    }
+    for (; j < n_out; j++) acc0 = fma(sg[j * 8 + lane], __ldg(Wi + j), acc0);
+    gx[o] = (acc0 + acc1) + (acc2 + acc3);
+  }
+  // gW[i][j] += sum over lanes of x[i] * gy[j]   (lane sum as reverse_batch, then one accumulate per frame)
+  for (int e = tid; e < n_in * n_out; e += nt) {
+    const int i = e / n_out, j = e - i * n_out;
+    const double *xi = sx + i * 8, *gj = sg + j * 8;
+    double r0 = xi[0] * gj[0], r1 = xi[1] * gj[1];
+    r0 = fma(xi[2], gj[2], r0);
+    r1 = fma(xi[3], gj[3], r1);
+    r0 = fma(xi[4], gj[4], r0);
+    r1 = fma(xi[5], gj[5], r1);
+    r0 = fma(xi[6], gj[6], r0);
+    r1 = fma(xi[7], gj[7], r1);
+    gW[e] += r0 + r1;
+  }
+  for (int j = tid; j < n_out; j += nt) {
+    const double *gj = sg + j * 8;
+    gb[j] += ((gj[0] + gj[1]) + (gj[2] + gj[3])) + ((gj[4] + gj[5]) + (gj[6] + gj[7]));
+  }
+  __syncthreads();
+}
+
 // The interpreter.  grid = tiles, block = W warps; dynamic shared memory = W slot rings.
 // record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21] | dual[22]
 // kRings = false: generic executables (every slot in the memory image, plain global loads/stores).
 template <int kMaxWarps, bool kRings, bool kStreamPrefetch>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
-                  uint64_t tile_stride, uint32_t ring_doubles, long long *trace) {
+                  uint64_t tile_stride, uint32_t ring_doubles, long long *trace, const double *__restrict__ pool,
+                  uint32_t pool_offset, uint32_t pool_doubles) {
   extern __shared__ double trx_rings[];
+  __shared__ double dense_x[128 * 8], dense_g[128 * 8];  // staged operand blocks of the dense operators
   uint32_t trace_level = 0;
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
@@ -61,7 +136,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
   uint32_t hdr = __ldg(pc);
   trxvm::Ctx c;
   c.m = m;
-  c.ring = trx_rings + (size_t)warp * ring_doubles;
+  // pool == nullptr: one ring per warp (chain-scheduled streams); otherwise one CTA-wide slot cache
+  // (ring + constant pool) shared by all warps of the level-scheduled streams
+  c.ring = pool ? trx_rings : trx_rings + (size_t)warp * ring_doubles;
+  if (kRings && pool) {
+    for (uint32_t e = threadIdx.x; e < pool_doubles; e += blockDim.x) trx_rings[pool_offset + e] = pool[e];
+    __syncthreads();
+  }
   c.rings = kRings;
   c.dual = false;
   c.preloaded = false;
@@ -104,7 +185,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       // block-cooperative record: every warp holds it at the same stream position
       const uint32_t *next = pc + 1 + nargs + 2;
       hdr = __ldg(next);
-      trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
+      const uint32_t n0 = __ldg(pc + 1 + nargs), n1 = __ldg(pc + 2 + nargs);
+      if (op == trx::OP_X_DENSE && n0 <= 128)
+        dense_forward_dev(pc + 1, m, dense_x);
+      else if (op == trx::OP_R_X_DENSE && n0 <= 128 && n1 <= 128)
+        dense_reverse_dev(pc + 1, m, dense_x, dense_g);
+      else
+        trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
       pc = next;
       continue;
     }
@@ -123,7 +210,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       c.lo = lane32 & 7;
     }
     c.a = pc + 1 + sub;
-    if (!kRings) trxvm::preload_args(c);
+    trxvm::preload_args(c);
     const uint32_t *next = pc + 1 + (c.dual ? 2 * nargs : nargs) * c.as;
     hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
     // the stream is read sequentially: pull the following lines towards L1 (and further ones into L2)
@@ -252,6 +339,7 @@ struct trx_program {
   uint64_t *d_stream_begin = nullptr;
   uint32_t *d_const_idx = nullptr;
   uint64_t *d_const_bits = nullptr;
+  double *d_pool = nullptr;  // constant pool of the on-chip slot cache (dummy allocation when empty)
   DevElem *d_elems[3] = {nullptr, nullptr, nullptr};
   uint32_t n_elems[3] = {0, 0, 0};
   int scalar_inputs = TRX_SCALAR_SHARED, scalar_outputs = TRX_SCALAR_SHARED;
@@ -380,6 +468,14 @@ const char *trx_op_signature(int i) {
 
 uint64_t trx_kernel_launch_count(void) { return g_launches.load(); }
 
+// development aid: per-level bundle counts of a generically lowered program (low 16 bits: bundles,
+// high 16 bits: block-cooperative records)
+trx_status trx_debug_level_info(const trx_program *p, uint32_t *out, uint64_t n) {
+  if (!p || !out) return fail(TRX_ERR_INVALID, "bad argument");
+  for (uint64_t i = 0; i < n && i < p->low.level_bundles.size(); i++) out[i] = p->low.level_bundles[i];
+  return TRX_OK;
+}
+
 // development aid: the next generic-VM launches record, for tile 0, the clock at which every warp
 // arrives at / leaves each level barrier.  n_words = capacity of the device buffer in 64-bit words.
 trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer) {
@@ -407,6 +503,8 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     trx::LowerOptions opt;
     if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_PREFETCH")) opt.prefetch_distance = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
     trx::lowerProgram(src, opt, p->low);
   } catch (const std::exception &e) {
     std::string msg = e.what();
@@ -432,6 +530,11 @@ static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int
   if ((s = upload(p->low.stream_begin, &p->d_stream_begin)) != TRX_OK) return s;
   if ((s = upload(p->low.const_idx, &p->d_const_idx)) != TRX_OK) return s;
   if ((s = upload(p->low.const_bits, &p->d_const_bits)) != TRX_OK) return s;
+  if (p->low.cta_ring) {
+    std::vector<double> pool = p->low.pool_values;
+    if (pool.empty()) pool.push_back(0.0);
+    if ((s = upload(pool, &p->d_pool)) != TRX_OK) return s;
+  }
   for (int which = 0; which < 3; which++) {
     const trx::PortLayout &L = p->layout(which);
     std::vector<DevElem> elems(L.elems.size());
@@ -495,6 +598,7 @@ void trx_program_destroy(trx_program *p) {
   cudaFree(p->d_stream_begin);
   cudaFree(p->d_const_idx);
   cudaFree(p->d_const_bits);
+  cudaFree(p->d_pool);
   for (auto *e : p->d_elems) cudaFree(e);
   delete p;
 }
@@ -608,16 +712,18 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
         TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
       }
-      trx_vm_kernel<16, true, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                            m->tile_stride, p->low.ring_doubles, nullptr);
+      if (p->low.cta_ring) smem = (size_t)p->low.ring_doubles * sizeof(double);
+      trx_vm_kernel<16, true, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(
+          p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, p->low.ring_doubles, g_trace,
+          p->low.cta_ring ? p->d_pool : nullptr, p->low.pool_offset_doubles, (uint32_t)p->low.pool_values.size());
     } else {
       static int sp = getenv("TRX_STREAM_PREFETCH") ? atoi(getenv("TRX_STREAM_PREFETCH")) : 1;
       if (sp)
         trx_vm_kernel<16, false, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                                  m->tile_stride, 0, g_trace);
+                                                                                  m->tile_stride, 0, g_trace, nullptr, 0, 0);
       else
         trx_vm_kernel<16, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                                   m->tile_stride, 0, g_trace);
+                                                                                   m->tile_stride, 0, g_trace, nullptr, 0, 0);
     }
     g_launches++;
   }

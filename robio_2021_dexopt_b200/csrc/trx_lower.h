@@ -21,8 +21,11 @@
 #include <algorithm>
 #include <cstdint>
 #include <functional>
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/trx_file.h"
@@ -85,6 +88,12 @@ struct LowerOptions {
   // software prefetch: operands of level L+D that already exist are pulled into L2 while level L runs
   // (the schedule is static, so the addresses are known); 0 = off
   uint32_t prefetch_distance = 2;
+  // CTA-wide on-chip slot cache (shared memory): a FIFO ring of the most recently produced lane-typed
+  // values plus a pool of the tape's distinct constants.  Every result is still written to the memory
+  // image (the reference's persist-everything contract); reads are served on chip when the lowering can
+  // prove the value is still there.  0 = off.
+  uint32_t ring_slots = 0;   // 64-byte slots
+  uint32_t pool_slots = 0;   // 64-byte slots for deduplicated constants
 };
 
 struct LoweredProgram {
@@ -98,6 +107,10 @@ struct LoweredProgram {
   uint64_t max_level_width = 0;
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
+  uint32_t cta_ring = 0;                // 1: ring_doubles is one CTA-wide cache (ring + constant pool), not per warp
+  std::vector<double> pool_values;      // initial contents of the constant pool (doubles), placed after the ring
+  uint32_t pool_offset_doubles = 0;
+  std::vector<uint32_t> level_bundles;  // per level: bundles | (coop records << 16)  (development aid)
   uint64_t n_ring_reads = 0, n_image_reads = 0, n_ring_only_writes = 0, n_dual_writes = 0, n_image_writes = 0;
   bool has_forward = false, has_reverse = false;
   PortLayout inputs, parameters, outputs;
@@ -300,6 +313,69 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   std::vector<uint32_t> lvl_insts;
   std::vector<Bundle> bundles;
   std::vector<uint64_t> load(W);
+
+  // ---- on-chip slot cache (see LowerOptions): static residency decisions, level by level
+  const bool use_cache = opt.ring_slots > 0;
+  struct RingState {
+    std::vector<int64_t> owner;                                          // per slot: byte address or -1
+    std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> where;   // address -> (slot, comps)
+    uint32_t head = 0;
+    void drop(uint64_t addr) {
+      auto it = where.find(addr);
+      if (it == where.end()) return;
+      for (uint32_t t = it->second.first; t < it->second.first + it->second.second; t++) owner[t] = -1;
+      where.erase(it);
+    }
+    uint32_t alloc(uint64_t addr, uint32_t comps) {
+      uint32_t n = (uint32_t)owner.size();
+      if (comps > n) return ~0u;
+      drop(addr);
+      if (head + comps > n) head = 0;
+      for (uint32_t t = head; t < head + comps; t++)
+        if (owner[t] >= 0) drop((uint64_t)owner[t]);
+      for (uint32_t t = head; t < head + comps; t++) owner[t] = (int64_t)addr;
+      where[addr] = {head, comps};
+      uint32_t r = head;
+      head += comps;
+      return r;
+    }
+  } ring;
+  ring.owner.assign(opt.ring_slots, -1);
+  std::unordered_map<uint64_t, uint32_t> pool_of_const;  // constant address -> pool slot
+  if (use_cache) {
+    out.cta_ring = 1;
+    out.pool_offset_doubles = opt.ring_slots * 8;
+    // distinct lane-typed constants of this program, first come first served
+    std::map<std::vector<uint64_t>, uint32_t> seen;
+    std::unordered_set<uint64_t> written;
+    for (auto &in : insts) {
+      const OpSig &sig = table[ops[in.op].opcode];
+      for (size_t k = 0; k < sig.args.size(); k++)
+        if (!sig.args[k].is_input) forEachKey(in, k, [&](uint64_t key) { written.insert(key); });
+    }
+    uint32_t used = 0;
+    for (auto &c : src.constants) {
+      if (c.lanes != 8 || c.size % 64 || written.count(c.address)) continue;
+      uint32_t comps = c.size / 64;
+      std::vector<uint64_t> bits(c.size / 8);
+      std::memcpy(bits.data(), src.const_data.data() + c.offset, c.size);
+      auto it = seen.find(bits);
+      if (it == seen.end()) {
+        if (used + comps > opt.pool_slots) continue;
+        it = seen.emplace(bits, used).first;
+        for (uint64_t b : bits) {
+          double d;
+          std::memcpy(&d, &b, 8);
+          out.pool_values.push_back(d);
+        }
+        used += comps;
+      }
+      pool_of_const[c.address] = it->second;
+    }
+    out.ring_doubles = opt.ring_slots * 8 + (uint32_t)out.pool_values.size();
+  }
+  auto ringEligible = [&](const OpRef &o, const ArgSig &a) { return o.lane_width == 8 && a.kind == ARG_T && a.comps > 0; };
+
   for (uint32_t level = 1; level <= n_levels; level++) {
     emitPrefetch(level + PD);
     lvl_insts.assign(order.begin() + level_count[level], order.begin() + level_count[level + 1]);
@@ -310,6 +386,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       return oa.lane_width < ob.lane_width;
     });
     bundles.clear();
+    uint32_t n_coop_level = 0;
     // block-cooperative instructions first: one record, replicated into every warp's stream
     for (size_t i = 0; i < lvl_insts.size(); i++) {
       const Inst &in = insts[lvl_insts[i]];
@@ -329,6 +406,9 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         throw std::runtime_error("unknown block operator " + d.name);
       }
       uint32_t na = (uint32_t)sig.args.size();
+      if (use_cache)
+        for (uint32_t k = 0; k < na; k++)
+          if (!sig.args[k].is_input) forEachKey(in, k, [&](uint64_t key) { ring.drop(key); });
       for (auto &s : streams) {
         s.push_back(HeaderBits::make(o.opcode, false, 1, na, true));
         for (uint32_t k = 0; k < na; k++) s.push_back((uint32_t)(src.code[in.code_at + k] / 8));
@@ -336,6 +416,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         s.push_back(imm1);
       }
       out.n_bundles++;
+      n_coop_level++;
     }
     lvl_insts.erase(std::remove_if(lvl_insts.begin(), lvl_insts.end(),
                                    [&](uint32_t i) { return table[ops[insts[i].op].opcode].coop; }),
@@ -354,6 +435,32 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       i = j;
     }
     out.n_bundles += bundles.size();
+    // results of this level go into the ring first (evicting the oldest values); the operands of this
+    // level are resolved afterwards, so a value evicted now is read from the memory image
+    std::unordered_map<uint64_t, uint32_t> out_slot;
+    if (use_cache)
+      for (uint32_t ii : lvl_insts) {
+        const Inst &in = insts[ii];
+        const OpRef &o = ops[in.op];
+        const OpSig &sig = table[o.opcode];
+        for (size_t k = 0; k < sig.args.size(); k++) {
+          if (sig.args[k].is_input) continue;
+          uint64_t addr = src.code[in.code_at + k];
+          if (ringEligible(o, sig.args[k])) {
+            uint32_t slot = ring.alloc(addr, sig.args[k].comps);
+            if (slot != ~0u) out_slot[addr] = slot;
+          } else {
+            ring.drop(addr);
+          }
+        }
+      }
+    // a level that produces more than the ring holds wraps around inside itself: results whose slot was
+    // taken again by a later result of the same level are written to the memory image only
+    for (auto it = out_slot.begin(); it != out_slot.end();) {
+      auto w = ring.where.find(it->first);
+      if (w == ring.where.end() || w->second.first != it->second) it = out_slot.erase(it);
+      else ++it;
+    }
     std::stable_sort(bundles.begin(), bundles.end(), [](const Bundle &a, const Bundle &b) { return a.cost > b.cost; });
     std::fill(load.begin(), load.end(), 0);
     for (auto &bd : bundles) {
@@ -363,18 +470,55 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       const OpSig &sig = table[bd.opcode];
       uint32_t na = (uint32_t)sig.args.size();
       uint32_t stride = bd.wide ? 32 : 4;
-      s.push_back(HeaderBits::make(bd.opcode, bd.wide, bd.count, na));
+      const OpRef bo{bd.opcode, bd.wide ? 1u : 8u};
+      bool dual = false;
+      if (use_cache && !bd.wide)
+        for (uint32_t i = 0; i < bd.count && !dual; i++) {
+          const Inst &in = insts[lvl_insts[bd.first + i]];
+          for (uint32_t k = 0; k < na; k++)
+            if (!sig.args[k].is_input && out_slot.count(src.code[in.code_at + k])) dual = true;
+        }
+      s.push_back(HeaderBits::make(bd.opcode, bd.wide, bd.count, na) | ((dual ? 1u : 0u) << 22));
       size_t base = s.size();
-      s.resize(base + (size_t)na * stride, 0);
+      s.resize(base + (size_t)na * stride * (dual ? 2 : 1), 0xffffffffu);
       for (uint32_t i = 0; i < bd.count; i++) {
         const Inst &in = insts[lvl_insts[bd.first + i]];
-        for (uint32_t k = 0; k < na; k++) s[base + (size_t)k * stride + i] = (uint32_t)(src.code[in.code_at + k] / 8);
+        for (uint32_t k = 0; k < na; k++) {
+          uint64_t addr = src.code[in.code_at + k];
+          uint32_t image_word = (uint32_t)(addr / 8), word = image_word;
+          if (use_cache && ringEligible(bo, sig.args[k])) {
+            if (sig.args[k].is_input) {
+              auto pc_it = pool_of_const.find(addr);
+              auto it = ring.where.find(addr);
+              if (it != ring.where.end() && it->second.second == sig.args[k].comps && !out_slot.count(addr)) {
+                word = 0x80000000u | (it->second.first * 8);
+                out.n_ring_reads++;
+              } else if (pc_it != pool_of_const.end()) {
+                word = 0x80000000u | (out.pool_offset_doubles + pc_it->second * 8);
+                out.n_ring_reads++;
+              } else {
+                out.n_image_reads++;
+              }
+            } else {
+              auto it = out_slot.find(addr);
+              if (it != out_slot.end()) {
+                word = 0x80000000u | (it->second * 8);
+                s[base + (size_t)(na + k) * stride + i] = image_word;  // write-through to the memory image
+                out.n_dual_writes++;
+              } else {
+                out.n_image_writes++;
+              }
+            }
+          }
+          s[base + (size_t)k * stride + i] = word;
+        }
       }
       // idle sub-slots repeat the first instruction's addresses so that address arithmetic stays in range
       for (uint32_t i = bd.count; i < stride; i++)
-        for (uint32_t k = 0; k < na; k++) s[base + (size_t)k * stride + i] = s[base + (size_t)k * stride];
+        for (uint32_t k = 0; k < na * (dual ? 2u : 1u); k++) s[base + (size_t)k * stride + i] = s[base + (size_t)k * stride];
     }
     for (auto &s : streams) s.push_back(HeaderBits::make(OP_BARRIER, false, 1, 0));
+    out.level_bundles.push_back((uint32_t)bundles.size() | (n_coop_level << 16));
   }
   for (auto &s : streams) s.push_back(HeaderBits::make(OP_END, false, 1, 0));
   out.stream_begin.assign(W + 1, 0);

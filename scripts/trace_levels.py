@@ -46,4 +46,14 @@ idle_frac = 1 - busy.clip(min=0).sum() / (dur.sum() * W)
 print("fraction of warp-time waiting at barriers", idle_frac)
 hist, edges = np.histogram(dur, bins=[0, 500, 1000, 2000, 3000, 5000, 10000, 20000, 50000, 1e9])
 for h, e0, e1 in zip(hist, edges[:-1], edges[1:]): print("  %7d..%7d cycles: %6d levels, %5.1f%% of time" % (e0, min(e1, 9999999), h, 100 * dur[(dur >= e0) & (dur < e1)].sum() / dur.sum()))
+info = np.zeros(nlev, dtype=np.uint32)
+L.trx_debug_level_info.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+L.trx_debug_level_info(xs[which]._h, info.ctypes.data, nlev)
+nb, nc = (info & 0xffff)[1:], (info >> 16)[1:]
+print("levels with coop records: %d, share of time %.1f%%" % ((nc > 0).sum(), 100 * dur[nc > 0].sum() / dur.sum()))
+for lo, hi in ((0, 1), (1, 2), (2, 4), (4, 8), (8, 16), (16, 32), (32, 64), (64, 100000)):
+    sel = (nb >= lo) & (nb < hi) & (nc == 0)
+    if sel.any(): print("  %5d..%5d bundles: %5d levels, mean %7.0f cycles, %5.1f%% of time" % (lo, hi, sel.sum(), dur[sel].mean(), 100 * dur[sel].sum() / dur.sum()))
+sel = nc > 0
+print("  coop levels: mean %7.0f cycles; bundles alongside mean %.1f" % (dur[sel].mean(), nb[sel].mean()))
 np.save(os.path.join(ROOT, "gpurun_out", "trace_%s.npy" % which), t)

@@ -58,6 +58,8 @@ int emu_program_create_from_blob(const void *blob, size_t bytes, int warps, emu_
     std::unique_ptr<emu_program> p(new emu_program());
     trx::LowerOptions opt;
     opt.n_warps = (uint32_t)warps;
+    if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
     trx::lowerProgram(src, opt, p->low);
     bool reverse_only = p->low.has_reverse && !p->low.has_forward;
     p->scalar_inputs = reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED;
@@ -124,6 +126,11 @@ int emu_memory_create(uint64_t lanes, emu_memory **out) {
   return TRX_OK;
 }
 void emu_memory_destroy(emu_memory *m) { delete m; }
+int emu_memory_peek(emu_memory *m, uint64_t tile, uint64_t address, void *dst, uint64_t bytes) {
+  if (tile >= m->n_tiles || address + bytes > m->tile_stride * 8) return fail(TRX_ERR_INVALID, "peek out of range");
+  std::memcpy(dst, (const uint8_t *)(m->mem.data() + tile * m->tile_stride) + address, bytes);
+  return TRX_OK;
+}
 
 static int scatter(const emu_program *p, emu_memory *m, int which, const double *wide, uint64_t bytes) {
   const trx::PortLayout &L = p->layout(which);
@@ -179,6 +186,8 @@ int emu_execute(const emu_program *p, emu_memory *m) {
     for (size_t i = 0; i < low.const_idx.size(); i++) std::memcpy(mem + low.const_idx[i], &low.const_bits[i], 8);
     uint32_t W = low.n_warps;
     std::vector<double> rings((size_t)W * std::max<uint32_t>(low.ring_doubles, 1), 0.0);
+    if (low.cta_ring)
+      for (size_t i = 0; i < low.pool_values.size(); i++) rings[low.pool_offset_doubles + i] = low.pool_values[i];
     std::vector<const uint32_t *> pc(W);
     for (uint32_t w = 0; w < W; w++) pc[w] = low.stream.data() + low.stream_begin[w];
     bool done = false;
@@ -213,7 +222,7 @@ int emu_execute(const emu_program *p, emu_memory *m) {
           for (int lane32 = 0; lane32 < 32; lane32++) {
             trxvm::Ctx c;
             c.m = mem;
-            c.ring = rings.data() + (size_t)w * low.ring_doubles;
+            c.ring = low.cta_ring ? rings.data() : rings.data() + (size_t)w * low.ring_doubles;
             c.nargs = nargs;
             c.dual = dual;
             c.rings = true;
