@@ -179,7 +179,7 @@ def main():
     bundle = pkg.build_dexsyn(kind=KIND, frames=FRAMES, hidden=HIDDEN, programs="prog,prep,bprop", fuse_dense=FUSE_DENSE)
     engine = pkg.CudaEngine(local_rank)
     obj = pkg.Objective(engine, bundle, lanes=LANES_PER_GPU, max_device_bytes=MAX_DEVICE_BYTES, fused=bool(FUSED),
-                        separate=bool(int(os.environ.get("BENCH_SEPARATE", 0))), scalar_rows=(rank == 0))
+                        separate=bool(int(os.environ.get("BENCH_SEPARATE", 1))), scalar_rows=(rank == 0))
     t_build = time.time() - t_build
     n_x = obj.n_x
     prog = bundle.view("prog")

@@ -157,6 +157,7 @@ inline void hostExec(const trxfile::Program &p, const DecodedInst &in,
     c.dual = false;
     c.rings = false;
     c.preloaded = false;
+    c.gpool = nullptr;
     c.a = args;
     c.as = 1;
     c.cs = (lw == 1) ? 1 : 8;

@@ -118,17 +118,20 @@ __device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, 
   __syncthreads();
 }
 
+__device__ __forceinline__ bool g_rec_trace_flag(const long long *trace) { return trace[(1ll << 20) - 1] != 0; }
+
 // The interpreter.  grid = tiles, block = W warps; dynamic shared memory = W slot rings.
 // record header: opcode[0:11) | wide[11] | n_sub-1[12:17) | n_args[17:21) | coop[21] | dual[22]
 // kRings = false: generic executables (every slot in the memory image, plain global loads/stores).
-template <int kMaxWarps, bool kRings, bool kStreamPrefetch>
+// kPool: argument words with bit 31 set index the program's constant pool in global memory.
+template <int kMaxWarps, bool kRings, bool kStreamPrefetch, bool kPool>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
                   uint64_t tile_stride, uint32_t ring_doubles, long long *trace, const double *__restrict__ pool,
                   uint32_t pool_offset, uint32_t pool_doubles) {
   extern __shared__ double trx_rings[];
   __shared__ double dense_x[128 * 8], dense_g[128 * 8];  // staged operand blocks of the dense operators
-  uint32_t trace_level = 0;
+  uint32_t trace_level = 0, rec_count = 0;
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
   const int lane32 = threadIdx.x & 31;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     __syncthreads();
   }
   c.rings = kRings;
+  c.gpool = (kRings || !kPool) ? nullptr : pool;
   c.dual = false;
   c.preloaded = false;
   while (true) {
@@ -210,7 +214,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       c.lo = lane32 & 7;
     }
     c.a = pc + 1 + sub;
+    long long rt0 = 0, rt1 = 0;
+    const bool rec_trace = trace && blockIdx.x == 0 && g_rec_trace_flag(trace);
+    if (rec_trace) rt0 = clock64();
     trxvm::preload_args(c);
+    if (rec_trace) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int k = 0; k < 12; k++) sum += (k < nargs) ? c.w[k] : 0;
+      asm volatile("{ .reg .u32 d; add.u32 d, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(rt1) : "r"(sum));
+    }
     const uint32_t *next = pc + 1 + (c.dual ? 2 * nargs : nargs) * c.as;
     hdr = __ldg(next);  // look ahead: the next header is in flight while this record executes
     // the stream is read sequentially: pull the following lines towards L1 (and further ones into L2)
@@ -221,6 +234,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     }
     if (sub < nsub) trxvm::exec(op, c);
     __syncwarp();  // chain-scheduled streams: the next record of this warp may read what this one wrote
+    if (rec_trace) {
+      // development aid: per-record breakdown {start, argument words arrived, done, opcode}; the stores of
+      // the record are still in flight at `done`, the loads are not
+      __threadfence_block();
+      long long rt2 = clock64();
+      if (lane32 == 0) {
+        long long *rec = trace + (1ll << 20) + ((long long)warp * 4096 + (rec_count & 4095)) * 4;
+        rec[0] = rt0;
+        rec[1] = rt1;
+        rec[2] = rt2;
+        rec[3] = (long long)op | ((long long)nsub << 16) | ((long long)trace_level << 32);
+      }
+      rec_count++;
+    }
     pc = next;
   }
 }
@@ -530,7 +557,7 @@ static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int
   if ((s = upload(p->low.stream_begin, &p->d_stream_begin)) != TRX_OK) return s;
   if ((s = upload(p->low.const_idx, &p->d_const_idx)) != TRX_OK) return s;
   if ((s = upload(p->low.const_bits, &p->d_const_bits)) != TRX_OK) return s;
-  if (p->low.cta_ring) {
+  if (p->low.cta_ring || p->low.global_pool) {
     std::vector<double> pool = p->low.pool_values;
     if (pool.empty()) pool.push_back(0.0);
     if ((s = upload(pool, &p->d_pool)) != TRX_OK) return s;
@@ -709,21 +736,24 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
     if (p->low.ring_doubles) {
       static bool attr_set = false;
       if (!attr_set) {
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
       }
       if (p->low.cta_ring) smem = (size_t)p->low.ring_doubles * sizeof(double);
-      trx_vm_kernel<16, true, true><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(
+      trx_vm_kernel<16, true, true, false><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(
           p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, p->low.ring_doubles, g_trace,
           p->low.cta_ring ? p->d_pool : nullptr, p->low.pool_offset_doubles, (uint32_t)p->low.pool_values.size());
     } else {
       static int sp = getenv("TRX_STREAM_PREFETCH") ? atoi(getenv("TRX_STREAM_PREFETCH")) : 1;
-      if (sp)
-        trx_vm_kernel<16, false, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                                  m->tile_stride, 0, g_trace, nullptr, 0, 0);
+      if (p->low.global_pool)
+        trx_vm_kernel<16, false, true, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, p->d_pool, 0, 0);
+      else if (sp)
+        trx_vm_kernel<16, false, true, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0);
       else
-        trx_vm_kernel<16, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(p->d_stream, p->d_stream_begin, m->d_mem,
-                                                                                   m->tile_stride, 0, g_trace, nullptr, 0, 0);
+        trx_vm_kernel<16, false, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0);
     }
     g_launches++;
   }

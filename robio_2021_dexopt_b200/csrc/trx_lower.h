@@ -87,7 +87,7 @@ struct LowerOptions {
   uint32_t n_warps = 16;
   // software prefetch: operands of level L+D that already exist are pulled into L2 while level L runs
   // (the schedule is static, so the addresses are known); 0 = off
-  uint32_t prefetch_distance = 2;
+  uint32_t prefetch_distance = 0;  // measured: no gain on B200 for these tapes (profiles/README.md)
   // CTA-wide on-chip slot cache (shared memory): a FIFO ring of the most recently produced lane-typed
   // values plus a pool of the tape's distinct constants.  Every result is still written to the memory
   // image (the reference's persist-everything contract); reads are served on chip when the lowering can
@@ -107,6 +107,7 @@ struct LoweredProgram {
   uint64_t max_level_width = 0;
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
+  uint32_t global_pool = 0;             // 1: pool_values live in global memory (no on-chip ring)
   uint32_t cta_ring = 0;                // 1: ring_doubles is one CTA-wide cache (ring + constant pool), not per warp
   std::vector<double> pool_values;      // initial contents of the constant pool (doubles), placed after the ring
   uint32_t pool_offset_doubles = 0;
@@ -316,6 +317,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
 
   // ---- on-chip slot cache (see LowerOptions): static residency decisions, level by level
   const bool use_cache = opt.ring_slots > 0;
+  const bool use_gpool = !use_cache && opt.pool_slots > 0;  // constant pool in global memory, no ring
   struct RingState {
     std::vector<int64_t> owner;                                          // per slot: byte address or -1
     std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> where;   // address -> (slot, comps)
@@ -342,9 +344,10 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   } ring;
   ring.owner.assign(opt.ring_slots, -1);
   std::unordered_map<uint64_t, uint32_t> pool_of_const;  // constant address -> pool slot
-  if (use_cache) {
-    out.cta_ring = 1;
-    out.pool_offset_doubles = opt.ring_slots * 8;
+  if (use_cache || use_gpool) {
+    out.cta_ring = use_cache ? 1 : 0;
+    out.global_pool = use_gpool ? 1 : 0;
+    out.pool_offset_doubles = use_cache ? opt.ring_slots * 8 : 0;
     // distinct lane-typed constants of this program, first come first served
     std::map<std::vector<uint64_t>, uint32_t> seen;
     std::unordered_set<uint64_t> written;
@@ -372,7 +375,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       }
       pool_of_const[c.address] = it->second;
     }
-    out.ring_doubles = opt.ring_slots * 8 + (uint32_t)out.pool_values.size();
+    if (use_cache) out.ring_doubles = opt.ring_slots * 8 + (uint32_t)out.pool_values.size();
   }
   auto ringEligible = [&](const OpRef &o, const ArgSig &a) { return o.lane_width == 8 && a.kind == ARG_T && a.comps > 0; };
 
@@ -486,6 +489,15 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         for (uint32_t k = 0; k < na; k++) {
           uint64_t addr = src.code[in.code_at + k];
           uint32_t image_word = (uint32_t)(addr / 8), word = image_word;
+          if (use_gpool && ringEligible(bo, sig.args[k]) && sig.args[k].is_input) {
+            auto pc_it = pool_of_const.find(addr);
+            if (pc_it != pool_of_const.end()) {
+              word = 0x80000000u | (pc_it->second * 8);
+              out.n_ring_reads++;
+            } else {
+              out.n_image_reads++;
+            }
+          }
           if (use_cache && ringEligible(bo, sig.args[k])) {
             if (sig.args[k].is_input) {
               auto pc_it = pool_of_const.find(addr);

@@ -31,8 +31,11 @@ struct Ctx {
   int nargs;           // number of arguments (rows) of the record
   bool dual;           // record has a second row of words per argument
   bool rings;          // false: every argument word is a memory-image slot (generic executables)
+  const double *gpool; // non-null: words with bit 31 set index the program's deduplicated constant pool
+                       // in global memory (small, shared by all tiles, L1-resident) instead of the image
   bool preloaded;      // argument words were fetched into w[] when the record started
   uint32_t w[12];      // (registers: every use indexes it with a compile-time constant)
+  uint32_t w2[12];     // second row of a dual record: memory-image slot of an output that also lives on chip
 };
 
 TRX_HD uint32_t argword(const Ctx &c, int k) { return c.preloaded ? c.w[k] : c.a[k * c.as]; }
@@ -41,17 +44,26 @@ TRX_HD void preload_args(Ctx &c) {
 #pragma unroll
   for (int k = 0; k < 12; k++)
     if (k < c.nargs) c.w[k] = c.a[k * c.as];
+  if (c.rings && c.dual) {
+#pragma unroll
+    for (int k = 0; k < 12; k++)
+      if (k < c.nargs) c.w2[k] = c.a[(c.nargs + k) * c.as];
+  }
   c.preloaded = true;
 }
 TRX_HD double *slotptr(const Ctx &c, uint32_t w) {
-  if (!c.rings) return c.m + w;
+  if (!c.rings) {
+    // gpool is a compile-time null in kernels instantiated without a pool: the test folds away
+    if (c.gpool != nullptr && (w & kRingFlag)) return const_cast<double *>(c.gpool) + (w & 0x7fffffffu);
+    return c.m + w;
+  }
   return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w);
 }
 TRX_HD double ld(const Ctx &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.cs + c.lo]; }
 TRX_HD void st(const Ctx &c, int k, int j, double v) {
   slotptr(c, argword(c, k))[j * c.cs + c.lo] = v;
   if (c.rings && c.dual) {
-    uint32_t w2 = c.a[(c.nargs + k) * c.as];
+    uint32_t w2 = c.preloaded ? c.w2[k] : c.a[(c.nargs + k) * c.as];
     if (w2 != kNoSlot) c.m[w2 + j * c.cs + c.lo] = v;
   }
 }

@@ -25,14 +25,32 @@ for it in range(2):
     r = xs["prog"].run(b.arrays["x"], mem); xs["prep"].execute(mem); g = xs["bprop"].run(r, mem)
 nlev = xs[which].stat("n_levels"); W = xs[which].stat("n_warps")
 ptr = ctypes.c_void_p()
-L.trx_debug_trace(nlev * W * 2 + 64, ctypes.byref(ptr))
+NW = (1 << 20) + 16 * 4096 * 4 + 64
+assert nlev * W * 2 < (1 << 20) - 1
+L.trx_debug_trace(NW, ctypes.byref(ptr))
+flag = torch.ones(1, dtype=torch.int64, device='cuda')
+ctypes.CDLL('libcudart.so').cudaMemcpy(ctypes.c_void_p(ptr.value + ((1 << 20) - 1) * 8), ctypes.c_void_p(flag.data_ptr()), ctypes.c_size_t(8), 3)
 if which == "prog": xs["prog"].run(b.arrays["x"], mem)
 elif which == "bprop": xs["bprop"].run(r, mem)
 torch.cuda.synchronize()
 buf = torch.empty(nlev * W * 2, dtype=torch.int64, device="cuda")
 ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(buf.data_ptr()), ptr, ctypes.c_size_t(nlev * W * 16), 3)
 t = buf.cpu().numpy().reshape(nlev, W, 2)
+recbuf = torch.empty(16 * 4096 * 4, dtype=torch.int64, device="cuda")
+ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(recbuf.data_ptr()), ctypes.c_void_p(ptr.value + (1 << 20) * 8), ctypes.c_size_t(16 * 4096 * 32), 3)
+rec = recbuf.cpu().numpy().reshape(16, 4096, 4)
 L.trx_debug_trace(0, None)
+valid = rec[:, :, 0] > 0
+args_t = (rec[:, :, 1] - rec[:, :, 0])[valid]
+exec_t = (rec[:, :, 2] - rec[:, :, 1])[valid]
+ops = (rec[:, :, 3] & 0xffff)[valid]
+print("records traced", valid.sum(), "arg fetch cycles mean/median/p90", args_t.mean(), np.median(args_t), np.percentile(args_t, 90), "exec mean/median/p90", exec_t.mean(), np.median(exec_t), np.percentile(exec_t, 90))
+names = [L.trx_op_name(i).decode() for i in range(L.trx_op_count())]
+import collections
+by = collections.defaultdict(list)
+for o, a, e in zip(ops, args_t, exec_t): by[int(o)].append((a, e))
+for o, v in sorted(by.items(), key=lambda kv: -sum(a + e for a, e in kv[1]))[:14]:
+    v = np.array(v); print("  %-34s n=%5d args %6.0f exec %7.0f" % (names[o] if o < len(names) else o, len(v), v[:, 0].mean(), v[:, 1].mean()))
 arrive, leave = t[:, :, 0], t[:, :, 1]
 rel = leave.max(axis=1)
 dur = np.diff(rel)

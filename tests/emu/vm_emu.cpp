@@ -227,6 +227,8 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             c.dual = dual;
             c.rings = true;
             c.preloaded = false;
+            c.gpool = low.global_pool ? low.pool_values.data() : nullptr;
+            c.rings = !low.global_pool && true;
             int sub;
             if (wide) {
               sub = lane32;
