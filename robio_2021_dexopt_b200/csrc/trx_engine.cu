@@ -31,6 +31,12 @@ long long *g_trace = nullptr;  // development aid (trx_debug_trace)
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
+// development knob: TRX_STAGED=0 runs generic executables on the kernel that reads its stream from global memory
+bool staged_streams() {
+  static int v = getenv("TRX_STAGED") ? atoi(getenv("TRX_STAGED")) : 1;
+  return v != 0;
+}
+
 trx_status fail(trx_status code, const std::string &msg) {
   g_last_error = msg;
   return code;
@@ -128,7 +134,7 @@ template <int kMaxWarps, bool kRings, bool kStreamPrefetch, bool kPool>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
                   uint64_t tile_stride, uint32_t ring_doubles, long long *trace, const double *__restrict__ pool,
-                  uint32_t pool_offset, uint32_t pool_doubles) {
+                  uint32_t pool_offset, uint32_t pool_doubles, uint32_t page_words) {
   extern __shared__ double trx_rings[];
   __shared__ double dense_x[128 * 8], dense_g[128 * 8];  // staged operand blocks of the dense operators
   uint32_t trace_level = 0, rec_count = 0;
@@ -174,6 +180,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     const bool wide = (hdr >> 11) & 1u;
     const int nsub = (int)((hdr >> 12) & 31u) + 1;
     const int nargs = (int)((hdr >> 17) & 15u);
+    if (op == trx::OP_PAGE) {
+      const uint32_t at = (uint32_t)(pc - (stream + stream_begin[warp]));
+      pc += page_words - (at & (page_words - 1));
+      hdr = __ldg(pc);
+      continue;
+    }
     if (op == trx::OP_PREFETCH) {
       // software prefetch record: one 128-byte line of the tile image per lane, into L2
       const uint32_t *next = pc + 33;
@@ -249,6 +261,126 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       rec_count++;
     }
     pc = next;
+  }
+}
+
+
+// The interpreter of generic executables with the instruction stream staged in shared memory.
+// Every warp walks its own stream; the stream is cut into pages of kPage words (records never straddle
+// a page, trx_lower.h) and kPages of them sit in a per-warp ring that cp.async refills kPages-1 pages
+// ahead of the interpreter.  Header and argument words then cost a shared-memory read instead of two
+// dependent L2 round trips per record; the only global latency left on a record's critical path is its
+// operands.
+template <int kMaxWarps, int kPage, int kPages>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+    trx_vm_staged_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
+                         uint64_t tile_stride, long long *trace) {
+  extern __shared__ __align__(16) uint32_t trx_pages[];  // [warp][kPages][kPage]
+  __shared__ double dense_x[128 * 8], dense_g[128 * 8];
+  constexpr uint32_t kRing = kPage * kPages;
+  uint32_t trace_level = 0;
+  double *m = mem + (uint64_t)blockIdx.x * tile_stride;
+  const int warp = threadIdx.x >> 5;
+  const int lane32 = threadIdx.x & 31;
+  const uint32_t *base = stream + stream_begin[warp];
+  const uint32_t n_pages = (uint32_t)((stream_begin[warp + 1] - stream_begin[warp]) / kPage);
+  uint32_t *sbuf = trx_pages + (size_t)warp * kRing;
+  // one commit group per page, also for pages past the end of the stream, so that the group count
+  // the waits rely on stays fixed
+  auto fetch = [&](uint32_t page) {
+    if (page < n_pages) {
+      const uint32_t *src = base + (size_t)page * kPage;
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(sbuf + (page % kPages) * kPage);
+#pragma unroll
+      for (int i = 0; i < kPage / 128; i++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (i * 32 + lane32) * 16),
+                     "l"(src + (i * 32 + lane32) * 4)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (uint32_t pg = 0; pg < kPages; pg++) fetch(pg);
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPages - 1) : "memory");
+  __syncwarp();
+  uint32_t pos = 0, cur_page = 0;
+  while (true) {
+    if ((pos / kPage) != cur_page) {
+      // the page just left is free: refill it with the page kPages ahead, then make sure the page
+      // being entered has arrived
+      __syncwarp();
+      fetch(cur_page + kPages);
+      cur_page++;
+      asm volatile("cp.async.wait_group %0;" ::"n"(kPages - 1) : "memory");
+      __syncwarp();
+    }
+    const uint32_t *pc = sbuf + (pos & (kRing - 1));
+    const uint32_t hdr = *pc;
+    const uint32_t op = hdr & 0x7ffu;
+    if (op == trx::OP_END) break;
+    if (op == trx::OP_BARRIER) {
+      pos += 1;
+      if (trace && blockIdx.x == 0) {  // development aid: arrival / release clocks per level
+        long long t0 = clock64();
+        int arrived = __syncthreads_count(1);
+        long long t1;
+        asm volatile("{ .reg .u32 d; add.u32 d, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(t1) : "r"(arrived));
+        if (lane32 == 0) {
+          trace[((size_t)trace_level * (blockDim.x / 32) + warp) * 2] = t0;
+          trace[((size_t)trace_level * (blockDim.x / 32) + warp) * 2 + 1] = t1;
+        }
+        trace_level++;
+        continue;
+      }
+      __syncthreads();
+      continue;
+    }
+    if (op == trx::OP_PAGE) {
+      pos = (pos | (kPage - 1)) + 1;
+      continue;
+    }
+    const bool wide = (hdr >> 11) & 1u;
+    const int nsub = (int)((hdr >> 12) & 31u) + 1;
+    const int nargs = (int)((hdr >> 17) & 15u);
+    if (op == trx::OP_PREFETCH) {
+      if (lane32 < nsub) {
+        const double *line = m + (size_t)pc[1 + lane32] * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+      }
+      pos += 33;
+      continue;
+    }
+    if ((hdr >> 21) & 1u) {
+      // block-cooperative record: every warp holds it at the same stream position
+      const uint32_t n0 = pc[1 + nargs], n1 = pc[2 + nargs];
+      if (op == trx::OP_X_DENSE && n0 <= 128)
+        dense_forward_dev(pc + 1, m, dense_x);
+      else if (op == trx::OP_R_X_DENSE && n0 <= 128 && n1 <= 128)
+        dense_reverse_dev(pc + 1, m, dense_x, dense_g);
+      else
+        trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
+      pos += 1 + nargs + 2;
+      continue;
+    }
+    // the record layout is a compile-time property of each branch: operand addresses become
+    // base + immediate, and exactly the operator's argument words are read from the staged page
+    if (wide) {
+      trxvm::CtxT<32, 1, true> c;
+      c.m = m;
+      c.nargs = nargs;
+      c.preloaded = false;
+      c.a = pc + 1 + lane32;
+      if (lane32 < nsub) trxvm::exec(op, c);
+      pos += 1 + nargs * 32;
+    } else {
+      trxvm::CtxT<4, 8, true> c;
+      c.m = m;
+      c.nargs = nargs;
+      c.preloaded = false;
+      c.lo = lane32 & 7;
+      c.a = pc + 1 + (lane32 >> 3);
+      if ((lane32 >> 3) < nsub) trxvm::exec(op, c);
+      pos += 1 + nargs * 4;
+    }
   }
 }
 
@@ -532,6 +664,7 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     if (const char *w = getenv("TRX_PREFETCH")) opt.prefetch_distance = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_CHAIN")) opt.chain_cap = (uint32_t)atoi(w);
     trx::lowerProgram(src, opt, p->low);
   } catch (const std::exception &e) {
     std::string msg = e.what();
@@ -650,6 +783,7 @@ trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *val
   else if (k == "n_constants") *value = p->low.const_idx.size();
   else if (k == "ring_doubles") *value = p->low.ring_doubles;
   else if (k == "n_prefetch_lines") *value = p->low.n_prefetch_lines;
+  else if (k == "n_chained") *value = p->low.n_chained;
   else if (k == "n_ring_reads") *value = p->low.n_ring_reads;
   else if (k == "n_image_reads") *value = p->low.n_image_reads;
   else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;
@@ -742,18 +876,30 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
       if (p->low.cta_ring) smem = (size_t)p->low.ring_doubles * sizeof(double);
       trx_vm_kernel<16, true, true, false><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(
           p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, p->low.ring_doubles, g_trace,
-          p->low.cta_ring ? p->d_pool : nullptr, p->low.pool_offset_doubles, (uint32_t)p->low.pool_values.size());
+          p->low.cta_ring ? p->d_pool : nullptr, p->low.pool_offset_doubles, (uint32_t)p->low.pool_values.size(),
+          p->low.page_words);
+    } else if (p->low.page_words == 512 && !p->low.global_pool && staged_streams()) {
+      // the product path: stream pages staged in shared memory
+      constexpr int kPages = 4;
+      static bool attr_set = false;
+      const size_t bytes = (size_t)16 * 512 * kPages * sizeof(uint32_t);
+      if (!attr_set) {
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        attr_set = true;
+      }
+      trx_vm_staged_kernel<16, 512, kPages><<<(unsigned)m->n_tiles, W * 32, (size_t)W * 512 * kPages * sizeof(uint32_t), stream>>>(
+          p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
     } else {
       static int sp = getenv("TRX_STREAM_PREFETCH") ? atoi(getenv("TRX_STREAM_PREFETCH")) : 1;
       if (p->low.global_pool)
         trx_vm_kernel<16, false, true, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
-            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, p->d_pool, 0, 0);
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, p->d_pool, 0, 0, p->low.page_words);
       else if (sp)
         trx_vm_kernel<16, false, true, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
-            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0);
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0, p->low.page_words);
       else
         trx_vm_kernel<16, false, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
-            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0);
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0, p->low.page_words);
     }
     g_launches++;
   }

@@ -94,6 +94,15 @@ struct LowerOptions {
   // prove the value is still there.  0 = off.
   uint32_t ring_slots = 0;   // 64-byte slots
   uint32_t pool_slots = 0;   // 64-byte slots for deduplicated constants
+  // dependent instructions whose only same-level producers sit in ONE lane-local instruction chain are
+  // appended to that chain instead of opening a new level: the chain's records run back to back on the
+  // same threads (thread = (sub-instruction, lane)), so program order replaces the block barrier.
+  // Maximum chain length; <= 1 turns chaining off.
+  uint32_t chain_cap = 1;
+  // stream pages (words, power of two; 0 = unpaged): no record straddles a page boundary and every
+  // warp's stream starts on one, so the kernel can stage whole pages in shared memory ahead of the
+  // interpreter and read record headers and argument words from there
+  uint32_t page_words = 512;
 };
 
 struct LoweredProgram {
@@ -107,6 +116,8 @@ struct LoweredProgram {
   uint64_t max_level_width = 0;
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
+  uint32_t page_words = 0;  // stream page size the records were laid out for (0 = unpaged)
+  uint64_t n_chained = 0;  // instructions appended to a chain (each saved a level boundary)
   uint32_t global_pool = 0;             // 1: pool_values live in global memory (no on-chip ring)
   uint32_t cta_ring = 0;                // 1: ring_doubles is one CTA-wide cache (ring + constant pool), not per warp
   std::vector<double> pool_values;      // initial contents of the constant pool (doubles), placed after the ring
@@ -172,7 +183,9 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     uint32_t op;      // index into ops
     uint64_t code_at; // position of the first argument in src.code
     uint32_t level;
+    uint32_t chain;   // chain id (kNoChain: not chainable), position = order of appearance in the level
   };
+  constexpr uint32_t kNoChain = 0xffffffffu;
   std::vector<Inst> insts;
   insts.reserve(src.n_instructions);
   {
@@ -182,7 +195,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       if (oi >= ops.size()) throw std::runtime_error("invalid op");  // engine.cpp:44-48
       size_t na = table[ops[oi].opcode].args.size();
       if (pc + 1 + na > src.code.size()) throw std::runtime_error("truncated instruction");
-      insts.push_back({(uint32_t)oi, pc + 1, 0});
+      insts.push_back({(uint32_t)oi, pc + 1, 0, kNoChain});
       pc += 1 + na;
     }
     if (insts.size() != src.n_instructions) throw std::runtime_error("instruction count mismatch");
@@ -219,6 +232,21 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     return (size_t)(std::lower_bound(addrs.begin(), addrs.end(), a) - addrs.begin());
   };
   std::vector<uint32_t> wlevel(addrs.size(), 0), rlevel(addrs.size(), 0);
+  // chain of the last writer / of the readers at rlevel (kNoChain when they belong to different chains)
+  const bool chaining = opt.chain_cap > 1 && opt.ring_slots == 0;
+  std::vector<uint32_t> wchain(chaining ? addrs.size() : 0, kNoChain), rchain(chaining ? addrs.size() : 0, kNoChain);
+  std::vector<uint32_t> chain_len;   // per chain
+  std::vector<uint8_t> chain_wide;   // per chain: scalar-typed (32 per warp) or lane-typed (4 x 8 lanes)
+  // lane-local: thread (sub-instruction, lane) touches only its own lane of every argument
+  auto laneLocal = [&](const OpRef &o, const OpSig &sig) {
+    if (sig.coop) return false;
+    for (auto &a : sig.args) {
+      if (a.kind == ARG_T) continue;
+      if (a.kind == ARG_S && o.lane_width == 1) continue;
+      return false;
+    }
+    return true;
+  };
   uint32_t n_levels = 0;
   // level of the last writer of each (non-block) input argument at the time it is read: decides
   // whether the operand already exists when a prefetch for it could be issued
@@ -227,25 +255,57 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     const OpSig &sig = table[ops[in.op].opcode];
     size_t na = sig.args.size();
     uint32_t lvl = 0;
+    uint32_t dep_chain = kNoChain;
+    bool dep_mixed = false;  // the dependencies at level `lvl` are not all in one chain
+    auto dep = [&](uint32_t l, uint32_t c) {
+      if (l == 0) return;
+      if (l > lvl) {
+        lvl = l;
+        dep_chain = c;
+        dep_mixed = (c == kNoChain);
+      } else if (l == lvl && (c != dep_chain || c == kNoChain)) {
+        dep_mixed = true;
+      }
+    };
     for (size_t k = 0; k < na; k++) {
       bool is_in = sig.args[k].is_input;
       uint32_t wl = 0;
       forEachKey(in, k, [&](uint64_t key) {
         size_t id = slotId(key);
         wl = std::max(wl, wlevel[id]);
-        if (is_in) lvl = std::max(lvl, wlevel[id]);
-        else lvl = std::max(lvl, std::max(wlevel[id], rlevel[id]));
+        dep(wlevel[id], chaining ? wchain[id] : kNoChain);
+        if (!is_in) dep(rlevel[id], chaining ? rchain[id] : kNoChain);
       });
       arg_wlevel[in.code_at + k] = wl;
       out.arg_bytes_per_tile += src.ops[in.op].args[k].size;
     }
-    in.level = lvl + 1;
+    const bool local = chaining && laneLocal(ops[in.op], sig);
+    const bool wide_op = ops[in.op].lane_width == 1;
+    if (local && lvl >= 1 && !dep_mixed && dep_chain != kNoChain && chain_wide[dep_chain] == (wide_op ? 1 : 0) &&
+        chain_len[dep_chain] < opt.chain_cap) {
+      in.level = lvl;
+      in.chain = dep_chain;
+      chain_len[dep_chain]++;
+      out.n_chained++;
+    } else {
+      in.level = lvl + 1;
+      if (local) {
+        in.chain = (uint32_t)chain_len.size();
+        chain_len.push_back(1);
+        chain_wide.push_back(wide_op ? 1 : 0);
+      }
+    }
     n_levels = std::max(n_levels, in.level);
     for (size_t k = 0; k < na; k++)
       if (sig.args[k].is_input)
         forEachKey(in, k, [&](uint64_t key) {
           size_t id = slotId(key);
-          rlevel[id] = std::max(rlevel[id], in.level);
+          if (in.level > rlevel[id]) {
+            rlevel[id] = in.level;
+            if (chaining) rchain[id] = in.chain;
+          } else if (chaining && in.level == rlevel[id] && rchain[id] != in.chain) {
+            rchain[id] = kNoChain;
+          }
         });
     for (size_t k = 0; k < na; k++)
       if (!sig.args[k].is_input)
@@ -253,9 +313,11 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
           size_t id = slotId(key);
           wlevel[id] = in.level;
           rlevel[id] = in.level;
+          if (chaining) wchain[id] = rchain[id] = in.chain;
         });
   }
   out.n_levels = n_levels;
+  out.page_words = opt.page_words;
 
   // ---- 4. bucket by level, then by (opcode, width), build bundles, distribute to warps
   std::vector<uint32_t> level_count(n_levels + 2, 0);
@@ -268,6 +330,15 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   }
   const uint32_t W = opt.n_warps;
   std::vector<std::vector<uint32_t>> streams(W);
+  const uint32_t PG = opt.page_words;
+  if (PG && ((PG & (PG - 1)) || PG < 512)) throw std::runtime_error("stream page size must be a power of two >= 512");
+  // make room for an n-word record: it must not straddle a page
+  auto room = [&](std::vector<uint32_t> &s, size_t n) {
+    if (!PG) return;
+    if (n > PG) throw std::runtime_error("record larger than a stream page");
+    if ((s.size() & (PG - 1)) + n > PG)
+      while (s.size() & (PG - 1)) s.push_back(HeaderBits::make(OP_PAGE, false, 1, 0));
+  };
   // 128-byte lines (index = byte address / 128) that level L reads and that exist `prefetch_distance`
   // levels earlier
   const uint32_t PD = opt.prefetch_distance;
@@ -297,6 +368,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     for (size_t i = 0; i < lines.size(); i += 32) {
       uint32_t n = (uint32_t)std::min<size_t>(32, lines.size() - i);
       auto &s = streams[w];
+      room(s, 33);
       s.push_back(HeaderBits::make(OP_PREFETCH, true, n, 0));
       for (uint32_t j = 0; j < 32; j++) s.push_back(lines[i + (j < n ? j : 0)]);
       w = (w + 1) % W;
@@ -306,11 +378,12 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   };
   for (uint32_t l = 1; l <= PD && l <= n_levels; l++) emitPrefetch(l);  // nothing runs before level 1: warm up
   struct Bundle {
-    uint16_t opcode;
     bool wide;
-    uint32_t first, count;  // range in the level's sorted list
+    uint32_t first, count;  // range in the level's sorted unit list
+    uint32_t len;           // records: one per chain position
     uint32_t cost;
   };
+  std::vector<uint32_t> unit_first, unit_order;
   std::vector<uint32_t> lvl_insts;
   std::vector<Bundle> bundles;
   std::vector<uint64_t> load(W);
@@ -413,6 +486,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         for (uint32_t k = 0; k < na; k++)
           if (!sig.args[k].is_input) forEachKey(in, k, [&](uint64_t key) { ring.drop(key); });
       for (auto &s : streams) {
+        room(s, na + 3);
         s.push_back(HeaderBits::make(o.opcode, false, 1, na, true));
         for (uint32_t k = 0; k < na; k++) s.push_back((uint32_t)(src.code[in.code_at + k] / 8));
         s.push_back(imm0);
@@ -424,20 +498,56 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     lvl_insts.erase(std::remove_if(lvl_insts.begin(), lvl_insts.end(),
                                    [&](uint32_t i) { return table[ops[insts[i].op].opcode].coop; }),
                     lvl_insts.end());
-    for (size_t i = 0; i < lvl_insts.size();) {
-      const OpRef &o = ops[insts[lvl_insts[i]].op];
+    // units = chains (or single instructions), members in program order; units with the same opcode
+    // sequence are packed side by side: 4 lane-typed or 32 scalar-typed units per warp
+    {
+      std::vector<std::pair<uint64_t, uint32_t>> keyed(lvl_insts.size());
+      for (size_t i = 0; i < lvl_insts.size(); i++) {
+        uint32_t c = insts[lvl_insts[i]].chain;
+        keyed[i] = {c == kNoChain ? (1ull << 32) + i : (uint64_t)c, lvl_insts[i]};
+      }
+      std::sort(keyed.begin(), keyed.end());  // by chain, then program order (instruction index)
+      unit_first.clear();
+      for (size_t i = 0; i < keyed.size(); i++) {
+        if (i == 0 || keyed[i].first != keyed[i - 1].first) unit_first.push_back((uint32_t)i);
+        lvl_insts[i] = keyed[i].second;
+      }
+      unit_first.push_back((uint32_t)keyed.size());
+    }
+    const size_t n_units = unit_first.size() - 1;
+    auto unitLen = [&](uint32_t u) { return unit_first[u + 1] - unit_first[u]; };
+    auto sigKey = [&](uint32_t u, uint32_t p) {
+      const OpRef &o = ops[insts[lvl_insts[unit_first[u] + p]].op];
+      return ((uint32_t)o.opcode << 4) | o.lane_width;
+    };
+    unit_order.resize(n_units);
+    for (uint32_t u = 0; u < n_units; u++) unit_order[u] = u;
+    auto unitCmp = [&](uint32_t x, uint32_t y) -> int {
+      uint32_t lx = unitLen(x), ly = unitLen(y);
+      for (uint32_t p = 0; p < lx && p < ly; p++) {
+        uint32_t kx = sigKey(x, p), ky = sigKey(y, p);
+        if (kx != ky) return kx < ky ? -1 : 1;
+      }
+      return lx == ly ? 0 : (lx < ly ? -1 : 1);
+    };
+    std::stable_sort(unit_order.begin(), unit_order.end(), [&](uint32_t x, uint32_t y) { return unitCmp(x, y) < 0; });
+    for (size_t i = 0; i < n_units;) {
+      uint32_t u = unit_order[i];
+      const OpRef &o = ops[insts[lvl_insts[unit_first[u]]].op];
       bool wide = (o.lane_width == 1);
       uint32_t cap = wide ? 32 : 4;
-      size_t j = i;
-      while (j < lvl_insts.size() && j - i < cap) {
-        const OpRef &o2 = ops[insts[lvl_insts[j]].op];
-        if (o2.opcode != o.opcode || o2.lane_width != o.lane_width) break;
-        j++;
-      }
-      bundles.push_back({o.opcode, wide, (uint32_t)i, (uint32_t)(j - i), table[o.opcode].cost + 8});
+      size_t j = i + 1;
+      while (j < n_units && j - i < cap && unitCmp(u, unit_order[j]) == 0) j++;
+      uint32_t cost = 0;
+      for (uint32_t p = 0; p < unitLen(u); p++) cost += table[ops[insts[lvl_insts[unit_first[u] + p]].op].opcode].cost + 8;
+      bundles.push_back({wide, (uint32_t)i, (uint32_t)(j - i), unitLen(u), cost});
+      out.n_bundles += unitLen(u);
       i = j;
     }
-    out.n_bundles += bundles.size();
+    // instruction of the bundle's i-th unit at chain position p
+    auto member = [&](const Bundle &bd, uint32_t i, uint32_t p) -> const Inst & {
+      return insts[lvl_insts[unit_first[unit_order[bd.first + i]] + p]];
+    };
     // results of this level go into the ring first (evicting the oldest values); the operands of this
     // level are resolved afterwards, so a value evicted now is read from the memory image
     std::unordered_map<uint64_t, uint32_t> out_slot;
@@ -470,22 +580,25 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       uint32_t w = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
       load[w] += bd.cost;
       auto &s = streams[w];
-      const OpSig &sig = table[bd.opcode];
+      for (uint32_t p = 0; p < bd.len; p++) {
+      const uint16_t opcode = ops[member(bd, 0, p).op].opcode;
+      const OpSig &sig = table[opcode];
       uint32_t na = (uint32_t)sig.args.size();
       uint32_t stride = bd.wide ? 32 : 4;
-      const OpRef bo{bd.opcode, bd.wide ? 1u : 8u};
+      const OpRef bo{opcode, bd.wide ? 1u : 8u};
       bool dual = false;
       if (use_cache && !bd.wide)
         for (uint32_t i = 0; i < bd.count && !dual; i++) {
-          const Inst &in = insts[lvl_insts[bd.first + i]];
+          const Inst &in = member(bd, i, p);
           for (uint32_t k = 0; k < na; k++)
             if (!sig.args[k].is_input && out_slot.count(src.code[in.code_at + k])) dual = true;
         }
-      s.push_back(HeaderBits::make(bd.opcode, bd.wide, bd.count, na) | ((dual ? 1u : 0u) << 22));
+      room(s, 1 + (size_t)na * stride * (dual ? 2 : 1));
+      s.push_back(HeaderBits::make(opcode, bd.wide, bd.count, na) | ((dual ? 1u : 0u) << 22));
       size_t base = s.size();
       s.resize(base + (size_t)na * stride * (dual ? 2 : 1), 0xffffffffu);
       for (uint32_t i = 0; i < bd.count; i++) {
-        const Inst &in = insts[lvl_insts[bd.first + i]];
+        const Inst &in = member(bd, i, p);
         for (uint32_t k = 0; k < na; k++) {
           uint64_t addr = src.code[in.code_at + k];
           uint32_t image_word = (uint32_t)(addr / 8), word = image_word;
@@ -528,6 +641,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       // idle sub-slots repeat the first instruction's addresses so that address arithmetic stays in range
       for (uint32_t i = bd.count; i < stride; i++)
         for (uint32_t k = 0; k < na * (dual ? 2u : 1u); k++) s[base + (size_t)k * stride + i] = s[base + (size_t)k * stride];
+      }
     }
     for (auto &s : streams) s.push_back(HeaderBits::make(OP_BARRIER, false, 1, 0));
     out.level_bundles.push_back((uint32_t)bundles.size() | (n_coop_level << 16));
@@ -537,8 +651,10 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   for (uint32_t w = 0; w < W; w++) {
     out.stream_begin[w] = out.stream.size();
     out.stream.insert(out.stream.end(), streams[w].begin(), streams[w].end());
-    // pad so that a one-record look-ahead never reads past the allocation
+    // pad so that a one-record look-ahead never reads past the allocation, and to whole pages
     for (int i = 0; i < 16; i++) out.stream.push_back(HeaderBits::make(OP_END, false, 1, 0));
+    if (PG)
+      while (out.stream.size() & (PG - 1)) out.stream.push_back(HeaderBits::make(OP_END, false, 1, 0));
   }
   out.stream_begin[W] = out.stream.size();
 

@@ -18,6 +18,7 @@ enum Opcode : uint16_t {
 #include "vm_ops.def"
 #undef TRX_OP
   OP_COUNT,
+  OP_PAGE = 0x7fc,      // continue at the next stream page (records never straddle a page)
   OP_PREFETCH = 0x7fd,  // 32 words: 128-byte line indices of the tile image to pull into L2
   OP_BARRIER = 0x7fe,
   OP_END = 0x7ff

@@ -21,7 +21,11 @@ namespace trxvm {
 static constexpr uint32_t kRingFlag = 0x80000000u;
 static constexpr uint32_t kNoSlot = 0xffffffffu;
 
-struct Ctx {
+// kAS / kCS: argument stride and component stride as compile-time constants (0 = run-time fields `as`
+// and `cs`).  kPlain: every argument word is a memory-image slot (no ring, no pool, no dual rows), so
+// an operand address is  m + 8 * (word + lane)  plus an immediate per component.
+template <int kAS, int kCS, bool kPlain>
+struct CtxT {
   double *m;           // base of this tile's memory image (global memory)
   double *ring;        // base of this warp's slot ring (shared memory)
   const uint32_t *a;   // first argument word of this thread's sub-instruction
@@ -36,88 +40,140 @@ struct Ctx {
   bool preloaded;      // argument words were fetched into w[] when the record started
   uint32_t w[12];      // (registers: every use indexes it with a compile-time constant)
   uint32_t w2[12];     // second row of a dual record: memory-image slot of an output that also lives on chip
+  TRX_HD int AS() const { return kAS ? kAS : as; }
+  TRX_HD int CS() const { return kCS ? kCS : cs; }
+  TRX_HD int LO() const { return kCS == 1 ? 0 : lo; }
+  TRX_HD bool RINGS() const { return kPlain ? false : rings; }
+  TRX_HD bool DUAL() const { return kPlain ? false : dual; }
+  TRX_HD const double *GPOOL() const { return kPlain ? nullptr : gpool; }
 };
+using Ctx = CtxT<0, 0, false>;
 
-TRX_HD uint32_t argword(const Ctx &c, int k) { return c.preloaded ? c.w[k] : c.a[k * c.as]; }
+template <class C>
+TRX_HD uint32_t argword(const C &c, int k) { return c.preloaded ? c.w[k] : c.a[k * c.AS()]; }
 // all argument words of the record at once: independent loads, one latency instead of one per operand
-TRX_HD void preload_args(Ctx &c) {
+template <class C>
+TRX_HD void preload_args(C &c) {
 #pragma unroll
   for (int k = 0; k < 12; k++)
-    if (k < c.nargs) c.w[k] = c.a[k * c.as];
-  if (c.rings && c.dual) {
+    if (k < c.nargs) c.w[k] = c.a[k * c.AS()];
+  if (c.RINGS() && c.DUAL()) {
 #pragma unroll
     for (int k = 0; k < 12; k++)
-      if (k < c.nargs) c.w2[k] = c.a[(c.nargs + k) * c.as];
+      if (k < c.nargs) c.w2[k] = c.a[(c.nargs + k) * c.AS()];
   }
   c.preloaded = true;
 }
-TRX_HD double *slotptr(const Ctx &c, uint32_t w) {
-  if (!c.rings) {
+// the same for an operator whose argument count is known where it is expanded (exec below)
+template <int kN, class C>
+TRX_HD void preload_n(C &c) {
+  if (c.preloaded) return;
+#pragma unroll
+  for (int k = 0; k < kN; k++) c.w[k] = c.a[k * c.AS()];
+  if (c.RINGS() && c.DUAL()) {
+#pragma unroll
+    for (int k = 0; k < kN; k++) c.w2[k] = c.a[(kN + k) * c.AS()];
+  }
+  c.preloaded = true;
+}
+template <class C>
+TRX_HD double *slotptr(const C &c, uint32_t w) {
+  if (!c.RINGS()) {
     // gpool is a compile-time null in kernels instantiated without a pool: the test folds away
-    if (c.gpool != nullptr && (w & kRingFlag)) return const_cast<double *>(c.gpool) + (w & 0x7fffffffu);
+    if (c.GPOOL() != nullptr && (w & kRingFlag)) return const_cast<double *>(c.GPOOL()) + (w & 0x7fffffffu);
     return c.m + w;
   }
   return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w);
 }
-TRX_HD double ld(const Ctx &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.cs + c.lo]; }
-TRX_HD void st(const Ctx &c, int k, int j, double v) {
-  slotptr(c, argword(c, k))[j * c.cs + c.lo] = v;
-  if (c.rings && c.dual) {
-    uint32_t w2 = c.preloaded ? c.w2[k] : c.a[(c.nargs + k) * c.as];
-    if (w2 != kNoSlot) c.m[w2 + j * c.cs + c.lo] = v;
+template <class C>
+TRX_HD double ld(const C &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.CS() + c.LO()]; }
+template <class C>
+TRX_HD void st(const C &c, int k, int j, double v) {
+  slotptr(c, argword(c, k))[j * c.CS() + c.LO()] = v;
+  if (c.RINGS() && c.DUAL()) {
+    uint32_t w2 = c.preloaded ? c.w2[k] : c.a[(c.nargs + k) * c.AS()];
+    if (w2 != kNoSlot) c.m[w2 + j * c.CS() + c.LO()] = v;
   }
 }
 // BatchScalar-typed argument: one double shared by the lanes (always in the memory image)
-TRX_HD double lds(const Ctx &c, int k) { return c.m[argword(c, k)]; }
+template <class C>
+TRX_HD double lds(const C &c, int k) { return c.m[argword(c, k)]; }
 // reverse of `batch`: da = sum of the lanes of dx, left to right (dexopt/src/ops.h:22-30)
-TRX_HD void sts_lanesum(const Ctx &c, int kout, int kin) {
-  if (c.lo != 0) return;
+template <class C>
+TRX_HD void sts_lanesum(const C &c, int kout, int kin) {
+  if (c.LO() != 0) return;
   const double *p = slotptr(c, argword(c, kin));
   double rs = 0.0;
-  int n = (c.cs == 8) ? 8 : 1;
+  int n = (c.CS() == 8) ? 8 : 1;
   for (int i = 0; i < n; i++) rs += p[i];
   c.m[argword(c, kout)] = rs;
 }
-TRX_HD V3 ldv(const Ctx &c, int k, int o) { return V3{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2)}; }
-TRX_HD Q4 ldq(const Ctx &c, int k, int o) { return Q4{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2), ld(c, k, o + 3)}; }
-TRX_HD PoseV ldp(const Ctx &c, int k, int o) {
+template <class C>
+TRX_HD V3 ldv(const C &c, int k, int o) { return V3{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2)}; }
+template <class C>
+TRX_HD Q4 ldq(const C &c, int k, int o) { return Q4{ld(c, k, o), ld(c, k, o + 1), ld(c, k, o + 2), ld(c, k, o + 3)}; }
+template <class C>
+TRX_HD PoseV ldp(const C &c, int k, int o) {
   PoseV p;
   p.t = ldv(c, k, o);
   p.r = ldq(c, k, o + 3);
   return p;
 }
-TRX_HD TwistV ldt(const Ctx &c, int k, int o) {
+template <class C>
+TRX_HD TwistV ldt(const C &c, int k, int o) {
   TwistV t;
   t.t = ldv(c, k, o);
   t.r = ldv(c, k, o + 3);
   return t;
 }
-TRX_HD void stv(const Ctx &c, int k, int o, const V3 &v) {
+template <class C>
+TRX_HD void stv(const C &c, int k, int o, const V3 &v) {
   st(c, k, o, v.x);
   st(c, k, o + 1, v.y);
   st(c, k, o + 2, v.z);
 }
-TRX_HD void stq(const Ctx &c, int k, int o, const Q4 &q) {
+template <class C>
+TRX_HD void stq(const C &c, int k, int o, const Q4 &q) {
   st(c, k, o, q.x);
   st(c, k, o + 1, q.y);
   st(c, k, o + 2, q.z);
   st(c, k, o + 3, q.w);
 }
-TRX_HD void stp(const Ctx &c, int k, int o, const PoseV &p) {
+template <class C>
+TRX_HD void stp(const C &c, int k, int o, const PoseV &p) {
   stv(c, k, o, p.t);
   stq(c, k, o + 3, p.r);
 }
-TRX_HD void stt(const Ctx &c, int k, int o, const TwistV &t) {
+template <class C>
+TRX_HD void stt(const C &c, int k, int o, const TwistV &t) {
   stv(c, k, o, t.t);
   stv(c, k, o + 3, t.r);
 }
 
-// One instruction.  `opcode` is warp-uniform, so the switch does not diverge.
-TRX_HD void exec(uint32_t opcode, const Ctx &c) {
+// number of arguments in a signature string (tokens separated by single blanks)
+constexpr int sigArgCount(const char *sig) {
+  int n = 0;
+  bool in_token = false;
+  for (const char *p = sig; *p; p++) {
+    if (*p == ' ') in_token = false;
+    else if (!in_token) {
+      in_token = true;
+      n++;
+    }
+  }
+  return n;
+}
+
+// One instruction.  `opcode` is warp-uniform, so the switch does not diverge.  The argument words
+// are fetched first, as many as the operator's signature names.
+template <class C>
+TRX_HD void exec(uint32_t opcode, C &c) {
   switch (opcode) {
-#define TRX_OP(ENUM, NAME, MODE, SIG, ...) \
-  case trx::OP_##ENUM: {                   \
-    __VA_ARGS__                            \
+#define TRX_OP(ENUM, NAME, MODE, SIG, ...)        \
+  case trx::OP_##ENUM: {                          \
+    constexpr int kNumArgs = sigArgCount(SIG);    \
+    preload_n<kNumArgs>(c);                       \
+    __VA_ARGS__                                   \
   } break;
 #include "vm_ops.def"
 #undef TRX_OP

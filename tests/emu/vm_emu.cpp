@@ -60,6 +60,7 @@ int emu_program_create_from_blob(const void *blob, size_t bytes, int warps, emu_
     opt.n_warps = (uint32_t)warps;
     if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_CHAIN")) opt.chain_cap = (uint32_t)atoi(w);
     trx::lowerProgram(src, opt, p->low);
     bool reverse_only = p->low.has_reverse && !p->low.has_forward;
     p->scalar_inputs = reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED;
@@ -206,6 +207,11 @@ int emu_execute(const emu_program *p, emu_memory *m) {
           }
           if (op == trx::OP_PREFETCH) {
             pc[w] += 33;
+            continue;
+          }
+          if (op == trx::OP_PAGE) {
+            size_t at = (size_t)(pc[w] - (low.stream.data() + low.stream_begin[w]));
+            pc[w] += low.page_words - (at & (low.page_words - 1));
             continue;
           }
           bool wide = (hdr >> 11) & 1u;
