@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
   extern __shared__ __align__(16) uint32_t trx_pages[];  // [warp][kPages][kPage]
   __shared__ double dense_x[128 * 8], dense_g[128 * 8];
   constexpr uint32_t kRing = kPage * kPages;
-  uint32_t trace_level = 0;
+  uint32_t trace_level = 0, rec_count = 0;
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
   const int lane32 = threadIdx.x & 31;
@@ -313,6 +313,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       asm volatile("cp.async.wait_group %0;" ::"n"(kPages - 1) : "memory");
       __syncwarp();
     }
+    const bool rec_trace = trace && blockIdx.x == 0 && g_rec_trace_flag(trace);
+    long long rt0 = 0, rt1 = 0;
+    if (rec_trace) rt0 = clock64();
     const uint32_t *pc = sbuf + (pos & (kRing - 1));
     const uint32_t hdr = *pc;
     const uint32_t op = hdr & 0x7ffu;
@@ -361,6 +364,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       pos += 1 + nargs + 2;
       continue;
     }
+    if (rec_trace) asm volatile("{ .reg .u32 d; add.u32 d, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(rt1) : "r"(hdr));
     // the record layout is a compile-time property of each branch: operand addresses become
     // base + immediate, and exactly the operator's argument words are read from the staged page
     if (wide) {
@@ -380,6 +384,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       c.a = pc + 1 + (lane32 >> 3);
       if ((lane32 >> 3) < nsub) trxvm::exec(op, c);
       pos += 1 + nargs * 4;
+    }
+    if (rec_trace) {
+      // development aid: per-record {start, header decoded, loads done, opcode}
+      __syncwarp();
+      __threadfence_block();
+      long long rt2 = clock64();
+      if (lane32 == 0) {
+        long long *rec = trace + (1ll << 20) + ((long long)warp * 4096 + (rec_count & 4095)) * 4;
+        rec[0] = rt0;
+        rec[1] = rt1;
+        rec[2] = rt2;
+        rec[3] = (long long)op | ((long long)nsub << 16) | ((long long)trace_level << 32);
+      }
+      rec_count++;
     }
   }
 }
@@ -452,13 +470,35 @@ struct SeedElem {
   uint32_t src, dst;
   uint32_t scalar;
 };
+constexpr int kSeedSplit = 8;  // blocks per tile (grid.y); partial sums are combined in a fixed order
 __global__ void trx_seed_kernel(const SeedElem *__restrict__ elems, uint32_t n, double *mem, uint64_t tile_stride,
                                 int first_chunk, double *__restrict__ partial) {
   __shared__ double red[256];
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   bool owner = first_chunk && blockIdx.x == 0;
+  const uint32_t per = (n + gridDim.y - 1) / gridDim.y;
+  const uint32_t begin = blockIdx.y * per, end = min(n, begin + per);
   double acc = 0.0;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+  uint32_t i = begin + threadIdx.x;
+  // four independent element chains in flight per thread (the table and the residual rows are both
+  // read once: latency, not reuse, is what limits this kernel)
+  for (; i + 3 * blockDim.x < end; i += 4 * blockDim.x) {
+    SeedElem e0 = elems[i], e1 = elems[i + blockDim.x], e2 = elems[i + 2 * blockDim.x], e3 = elems[i + 3 * blockDim.x];
+    double v0 = m[e0.src], v1 = m[e1.src], v2 = m[e2.src], v3 = m[e3.src];
+    if (e0.scalar && !owner) v0 = 0.0;
+    if (e1.scalar && !owner) v1 = 0.0;
+    if (e2.scalar && !owner) v2 = 0.0;
+    if (e3.scalar && !owner) v3 = 0.0;
+    m[e0.dst] = v0;
+    m[e1.dst] = v1;
+    m[e2.dst] = v2;
+    m[e3.dst] = v3;
+    acc += v0 * v0;
+    acc += v1 * v1;
+    acc += v2 * v2;
+    acc += v3 * v3;
+  }
+  for (; i < end; i += blockDim.x) {
     SeedElem e = elems[i];
     double v = m[e.src];
     if (e.scalar && !owner) v = 0.0;
@@ -471,7 +511,7 @@ __global__ void trx_seed_kernel(const SeedElem *__restrict__ elems, uint32_t n, 
     if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = red[0];
 }
 // fixed-order sum of the per-tile partials: out[0] (+)= sum
 __global__ void trx_loss_kernel(const double *__restrict__ partial, uint32_t n, double *out) {
@@ -890,15 +930,11 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
       trx_vm_staged_kernel<16, 512, kPages><<<(unsigned)m->n_tiles, W * 32, (size_t)W * 512 * kPages * sizeof(uint32_t), stream>>>(
           p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
     } else {
-      static int sp = getenv("TRX_STREAM_PREFETCH") ? atoi(getenv("TRX_STREAM_PREFETCH")) : 1;
       if (p->low.global_pool)
         trx_vm_kernel<16, false, true, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, p->d_pool, 0, 0, p->low.page_words);
-      else if (sp)
-        trx_vm_kernel<16, false, true, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
-            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0, p->low.page_words);
       else
-        trx_vm_kernel<16, false, false, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
+        trx_vm_kernel<16, false, true, false><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, nullptr, 0, 0, p->low.page_words);
     }
     g_launches++;
@@ -1095,7 +1131,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
   TRX_CUDA(cudaMalloc(&o->d_params, std::max<uint64_t>(1, o->param_elems) * 8));
   TRX_CUDA(cudaMemset(o->d_params, 0, std::max<uint64_t>(1, o->param_elems) * 8));
   TRX_CUDA(cudaMalloc(&o->d_out, (o->n_x + 1) * 8));
-  TRX_CUDA(cudaMalloc(&o->d_partial, tiles * 8));
+  TRX_CUDA(cudaMalloc(&o->d_partial, tiles * kSeedSplit * 8));
   TRX_CUDA(cudaMallocHost(&o->h_x, std::max<uint64_t>(1, o->n_x) * 8));
   TRX_CUDA(cudaMallocHost(&o->h_out, (o->n_x + 1) * 8));
   for (auto &e : o->ev) TRX_CUDA(cudaEventCreate(&e));
@@ -1189,8 +1225,9 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
     if (pe) cudaEventRecord(pe[0], stream);
     if ((s = trx_execute(o->prog, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[1], stream);
-    trx_seed_kernel<<<(unsigned)chunk_tiles, 256, 0, stream>>>(o->d_seed, o->n_seed, m->d_mem, m->tile_stride,
-                                                              (c == 0 && o->scalar_rows) ? 1 : 0, o->d_partial + c * chunk_tiles);
+    trx_seed_kernel<<<dim3((unsigned)chunk_tiles, kSeedSplit), 256, 0, stream>>>(
+        o->d_seed, o->n_seed, m->d_mem, m->tile_stride, (c == 0 && o->scalar_rows) ? 1 : 0,
+        o->d_partial + c * chunk_tiles * kSeedSplit);
     g_launches++;
     if (o->prep && (s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[2], stream);
@@ -1202,7 +1239,7 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
                                                m->tile_stride, (uint32_t)chunk_tiles, 1, c == 0 ? 0 : 1);
     g_launches++;
   }
-  trx_loss_kernel<<<1, 256, 0, stream>>>(o->d_partial, (uint32_t)(o->lanes / 8), d_out);
+  trx_loss_kernel<<<1, 256, 0, stream>>>(o->d_partial, (uint32_t)(o->lanes / 8) * kSeedSplit, d_out);
   g_launches++;
   TRX_CUDA(cudaGetLastError());
   return TRX_OK;

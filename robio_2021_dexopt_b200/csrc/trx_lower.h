@@ -98,7 +98,7 @@ struct LowerOptions {
   // appended to that chain instead of opening a new level: the chain's records run back to back on the
   // same threads (thread = (sub-instruction, lane)), so program order replaces the block barrier.
   // Maximum chain length; <= 1 turns chaining off.
-  uint32_t chain_cap = 1;
+  uint32_t chain_cap = 3;  // measured on B200 (profiles/README.md): 2..4 are within 2%, longer chains lose to load imbalance
   // stream pages (words, power of two; 0 = unpaged): no record straddles a page boundary and every
   // warp's stream starts on one, so the kernel can stage whole pages in shared memory ahead of the
   // interpreter and read record headers and argument words from there
@@ -117,6 +117,7 @@ struct LoweredProgram {
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
   uint32_t page_words = 0;  // stream page size the records were laid out for (0 = unpaged)
+  uint64_t n_dropped = 0;  // instructions without outputs, not lowered
   uint64_t n_chained = 0;  // instructions appended to a chain (each saved a level boundary)
   uint32_t global_pool = 0;             // 1: pool_values live in global memory (no on-chip ring)
   uint32_t cta_ring = 0;                // 1: ring_doubles is one CTA-wide cache (ring + constant pool), not per warp
@@ -188,6 +189,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   constexpr uint32_t kNoChain = 0xffffffffu;
   std::vector<Inst> insts;
   insts.reserve(src.n_instructions);
+  uint64_t n_decoded = 0;
   {
     uint64_t pc = 0;
     while (pc < src.code.size()) {
@@ -195,12 +197,18 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       if (oi >= ops.size()) throw std::runtime_error("invalid op");  // engine.cpp:44-48
       size_t na = table[ops[oi].opcode].args.size();
       if (pc + 1 + na > src.code.size()) throw std::runtime_error("truncated instruction");
-      insts.push_back({(uint32_t)oi, pc + 1, 0, kNoChain});
+      // an instruction without an output argument has no effect (the prepare rules of operators whose
+      // reverse rule needs nothing saved, e.g. prepare_add): it is counted but not lowered
+      bool has_output = false;
+      for (auto &a : table[ops[oi].opcode].args) has_output |= !a.is_input;
+      n_decoded++;
+      if (has_output) insts.push_back({(uint32_t)oi, pc + 1, 0, kNoChain});
+      else out.n_dropped++;
       pc += 1 + na;
     }
-    if (insts.size() != src.n_instructions) throw std::runtime_error("instruction count mismatch");
+    if (n_decoded != src.n_instructions) throw std::runtime_error("instruction count mismatch");
   }
-  out.n_instructions = insts.size();
+  out.n_instructions = n_decoded;
 
   // ---- 3. levels (ASAP) with RAW / WAR / WAW edges keyed by argument start address
   // an argument is tracked by its start address; block arguments by the start address of every element
