@@ -40,6 +40,8 @@ UNIT = "timestep*rollouts/s"
 # compulsory HBM traffic per timestep*rollout with one state checkpoint written by
 # the forward sweep and read back by the adjoint: 2 * 8 * (n_q + 13 * n_dyn) bytes, n_q = 29, n_dyn = 1
 B_ALG = 2 * 8 * (29 + 13)
+# measured DRAM traffic of the adjoint launch per unit (profiles/README.md): 3.894 GB / (32 frames * 1024 rollouts)
+NCU_BPROP_DRAM_BYTES_PER_UNIT = 3.893933e9 / (32 * 1024)
 
 
 def measured_peak_hbm():
@@ -281,8 +283,13 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "trx_vm_kernel (adjoint launch)", "lowering": "fused (chain schedule + slot rings)" if FUSED else "generic (levels)", "peak_source": peak_source,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the adjoint launch from the committed ncu --set full
+            # capture (profiles/ncu_full_r1_staged_T32_raw.csv: 3.894 GB for 32 frames x 1024 rollouts), scaled
+            # to this launch's units; only for the default dense-fused generic lowering it was captured on
+            "traffic": (NCU_BPROP_DRAM_BYTES_PER_UNIT * units_per_launch if (not FUSED and FUSE_DENSE) else None),
+            "traffic_source": "profiles/ncu_full_r1_staged_T32_raw.csv, per unit x units_per_launch",
+            "kernel": ("trx_vm_kernel" if FUSED else "trx_vm_staged_kernel") + " (adjoint launch)", "lowering": "fused (chain schedule + slot rings)" if FUSED else "generic (levels of chains; stream pages staged in shared memory)", "peak_source": peak_source,
             "algorithmic_bytes_per_unit": B_ALG / 2, "units_per_launch": units_per_launch,
             "launch_ms": bprop_ms_per_launch,
             "kernel_ms_per_step": {"prog": kernel_ms[0] / args.steps, "prep_seed": kernel_ms[1] / args.steps,
