@@ -298,7 +298,7 @@ def main():
             "interpreted_tape_gbs": tape_bytes / (8.0 * FRAMES) * units / world / (sum(kernel_ms) / args.steps * 1e-3) / 1e9,
         },
         "loss": loss,
-        "lowering_stats": {k: {q: obj.info("%s.%s" % (k, q)) for q in ("n_instructions", "n_levels", "n_bundles", "stream_words", "n_ring_reads", "n_image_reads", "n_ring_only_writes", "n_dual_writes", "n_image_writes", "n_prefetch_lines", "n_chained")} for k in ("prog", "prep", "bprop")},
+        "lowering_stats": {k: {q: obj.info("%s.%s" % (k, q)) for q in ("n_instructions", "n_levels", "n_bundles", "stream_words", "n_ring_reads", "n_image_reads", "n_ring_only_writes", "n_dual_writes", "n_image_writes", "n_prefetch_lines", "n_chained", "n_folded")} for k in ("prog", "prep", "bprop")},
         "setup_s": t_build,
         "chunks": n_chunks,
         "device_bytes": obj.info("device_bytes"),

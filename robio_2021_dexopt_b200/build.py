@@ -18,6 +18,9 @@ OUT = os.path.join(HERE, "libtrx_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # the interpreter's opcode switch is dense: let NVVM emit one brx.idx jump table for it instead of a
+    # compare tree in front of small tables (the default density threshold of 101 % never does)
+    "--jump-table-density=25",
 ]
 
 

@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     const uint32_t *pc = sbuf + (pos & (kRing - 1));
     const uint32_t hdr = *pc;
     const uint32_t op = hdr & 0x7ffu;
+    const bool wide = (hdr >> 11) & 1u;
+    const int nsub = (int)((hdr >> 12) & 31u) + 1;
+    const int nargs = (int)((hdr >> 17) & 15u);
+    // one test keeps the common case (an operator record) clear of the special words
+    if (op >= trx::OP_PAGE || ((hdr >> 21) & 1u)) {
     if (op == trx::OP_END) break;
     if (op == trx::OP_BARRIER) {
       pos += 1;
@@ -341,9 +346,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       pos = (pos | (kPage - 1)) + 1;
       continue;
     }
-    const bool wide = (hdr >> 11) & 1u;
-    const int nsub = (int)((hdr >> 12) & 31u) + 1;
-    const int nargs = (int)((hdr >> 17) & 15u);
     if (op == trx::OP_PREFETCH) {
       if (lane32 < nsub) {
         const double *line = m + (size_t)pc[1 + lane32] * 16;
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
       pos += 1 + nargs + 2;
       continue;
+    }
     }
     if (rec_trace) asm volatile("{ .reg .u32 d; add.u32 d, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(rt1) : "r"(hdr));
     // the record layout is a compile-time property of each branch: operand addresses become
@@ -693,7 +696,7 @@ static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int
                                 trx_program **out);
 
 static trx_status createFromFile(const trxfile::Program &src, int device, int scalar_in, int scalar_out,
-                                 trx_program **out) {
+                                 trx_program **out, bool fold_accumulate = false) {
   if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
   *out = nullptr;
   std::unique_ptr<trx_program> p(new trx_program());
@@ -705,6 +708,10 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_CHAIN")) opt.chain_cap = (uint32_t)atoi(w);
+    // folding needs the plain argument-word format of the staged kernel
+    static int fold_env = getenv("TRX_FOLD") ? atoi(getenv("TRX_FOLD")) : 1;
+    opt.fold_accumulate = fold_accumulate && fold_env && staged_streams() && opt.ring_slots == 0 && opt.pool_slots == 0 &&
+                          opt.page_words == 512;
     trx::lowerProgram(src, opt, p->low);
   } catch (const std::exception &e) {
     std::string msg = e.what();
@@ -824,6 +831,7 @@ trx_status trx_program_stat(const trx_program *p, const char *key, uint64_t *val
   else if (k == "ring_doubles") *value = p->low.ring_doubles;
   else if (k == "n_prefetch_lines") *value = p->low.n_prefetch_lines;
   else if (k == "n_chained") *value = p->low.n_chained;
+  else if (k == "n_folded") *value = p->low.n_folded;
   else if (k == "n_ring_reads") *value = p->low.n_ring_reads;
   else if (k == "n_image_reads") *value = p->low.n_image_reads;
   else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;
@@ -1075,7 +1083,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       o->prog = raw;
       if ((s = createFromFile(p_prep, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
       o->prep = raw;
-      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw, true)) != TRX_OK) return s;
       o->bprop = raw;
     } else {
       // default: x_prep interleaved into x_prog (every prepare instruction directly after its compute
@@ -1090,7 +1098,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       if ((s = createFromFile(combined, device, TRX_SCALAR_SHARED, TRX_SCALAR_SHARED, &raw)) != TRX_OK) return s;
       o->prog = raw;
       o->prep = nullptr;
-      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
+      if ((s = createFromFile(p_bprop, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw, true)) != TRX_OK) return s;
       o->bprop = raw;
     }
   }

@@ -98,11 +98,21 @@ struct LowerOptions {
   // appended to that chain instead of opening a new level: the chain's records run back to back on the
   // same threads (thread = (sub-instruction, lane)), so program order replaces the block barrier.
   // Maximum chain length; <= 1 turns chaining off.
-  uint32_t chain_cap = 3;  // measured on B200 (profiles/README.md): 2..4 are within 2%, longer chains lose to load imbalance
+  uint32_t chain_cap = 2;  // measured on B200 (profiles/README.md): 2..4 are within 3%, longer chains lose to load imbalance
   // stream pages (words, power of two; 0 = unpaged): no record straddles a page boundary and every
   // warp's stream starts on one, so the kernel can stage whole pages in shared memory ahead of the
   // interpreter and read record headers and argument words from there
   uint32_t page_words = 512;
+  // accumulate folding (adjoint tapes inside an objective, where nothing but ports crosses programs).
+  // The reference accumulates a second gradient contribution as
+  //     rop -> tmp ; move g -> t2 ; add t2, tmp -> g          (gradients.cpp:120-179)
+  // because its operators never alias an output with an input.  Here every operator loads all inputs
+  // before it stores, so the copy is dropped and the add runs in place:  add g, tmp -> g.  Likewise
+  //     rop -> tmp ; move tmp -> g      becomes      rop -> g.
+  // The dropped temporaries have one writer, one reader and are no port.  Values and summation order of
+  // every surviving slot are unchanged.  (Folding the add itself into rop's store was measured slower:
+  // the read-modify-write per component serialises behind rop's other stores.)
+  bool fold_accumulate = false;
 };
 
 struct LoweredProgram {
@@ -117,6 +127,7 @@ struct LoweredProgram {
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
   uint32_t page_words = 0;  // stream page size the records were laid out for (0 = unpaged)
+  uint64_t n_folded = 0;   // move/add instructions folded into their producer's output (fold_accumulate)
   uint64_t n_dropped = 0;  // instructions without outputs, not lowered
   uint64_t n_chained = 0;  // instructions appended to a chain (each saved a level boundary)
   uint32_t global_pool = 0;             // 1: pool_values live in global memory (no on-chip ring)
@@ -210,11 +221,146 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   }
   out.n_instructions = n_decoded;
 
+  // ---- 2b. accumulate folding (see LowerOptions)
+  std::vector<uint64_t> code(src.code);        // argument addresses after folding
+  if (opt.fold_accumulate && opt.ring_slots == 0 && opt.pool_slots == 0) {
+    struct SlotUse {
+      uint32_t writer = 0, reader = 0;
+      uint32_t nw = 0, nr = 0;
+    };
+    std::unordered_map<uint64_t, SlotUse> use;
+    use.reserve(src.code.size());
+    for (uint32_t i = 0; i < insts.size(); i++) {
+      const Inst &in = insts[i];
+      const OpSig &sig = table[ops[in.op].opcode];
+      for (size_t k = 0; k < sig.args.size(); k++) {
+        uint64_t addr = src.code[in.code_at + k];
+        if (isBlock(sig.args[k].kind)) {
+          uint32_t eb = blockElemBytes(sig.args[k].kind, 8), size = src.ops[in.op].args[k].size;
+          for (uint32_t off = 0; off < size; off += eb) {
+            SlotUse &u = use[addr + off];
+            u.nw += 2;
+            u.nr += 2;
+          }
+          continue;
+        }
+        SlotUse &u = use[addr];
+        if (sig.args[k].is_input) {
+          u.nr++;
+          u.reader = i;
+        } else {
+          u.nw++;
+          u.writer = i;
+        }
+      }
+    }
+    std::vector<std::pair<uint64_t, uint64_t>> port_ranges;
+    for (auto *ports : {&src.inputs, &src.parameters, &src.outputs, &src.constants})
+      for (auto &p : *ports) port_ranges.push_back({p.address, p.address + p.size});
+    std::sort(port_ranges.begin(), port_ranges.end());
+    {  // merge overlapping ranges: afterwards only the range starting last before the query can overlap it
+      size_t w = 0;
+      for (size_t i = 0; i < port_ranges.size(); i++) {
+        if (w && port_ranges[i].first <= port_ranges[w - 1].second)
+          port_ranges[w - 1].second = std::max(port_ranges[w - 1].second, port_ranges[i].second);
+        else
+          port_ranges[w++] = port_ranges[i];
+      }
+      port_ranges.resize(w);
+    }
+    auto inPort = [&](uint64_t a, uint64_t size) {
+      auto it = std::lower_bound(port_ranges.begin(), port_ranges.end(), std::make_pair(a + size, (uint64_t)0));
+      if (it == port_ranges.begin()) return false;
+      --it;
+      return it->second > a;
+    };
+    auto isMove = [](uint16_t o) {
+      return o == OP_MOVE || o == OP_MOVE_MAT3 || o == OP_MOVE_VEC3 || o == OP_MOVE_QUAT || o == OP_MOVE_POSE || o == OP_MOVE_TWIST;
+    };
+    auto isAdd = [](uint16_t o) { return o == OP_ADD || o == OP_ADD_VEC3 || o == OP_ADD_TWIST; };
+    std::vector<uint8_t> dropped(insts.size(), 0);
+    // a slot with exactly one writer and one reader (instruction `reader`): returns the writer or ~0u
+    auto soleWriter = [&](uint64_t addr, uint32_t reader) -> uint32_t {
+      auto it = use.find(addr);
+      if (it == use.end() || it->second.nw != 1 || it->second.nr != 1 || it->second.reader != reader) return ~0u;
+      return it->second.writer;
+    };
+    for (uint32_t bi = 0; bi < insts.size(); bi++) {
+      const Inst &B = insts[bi];
+      const OpRef &bo = ops[B.op];
+      if (!isMove(bo.opcode) && !isAdd(bo.opcode)) continue;
+      const uint32_t comps = table[bo.opcode].args[0].comps;
+      const uint64_t bytes = (uint64_t)comps * 8 * bo.lane_width;
+      // nothing in (from, bi) other than `skip` may touch dst
+      auto untouched = [&](uint32_t from, uint32_t skip, uint64_t dst) {
+        for (uint32_t j = from + 1; j < bi; j++) {
+          if (j == skip) continue;
+          const Inst &J = insts[j];
+          const OpSig &jsig = table[ops[J.op].opcode];
+          if (jsig.coop) return false;
+          for (size_t k = 0; k < jsig.args.size(); k++)
+            if (code[J.code_at + k] == dst || src.code[J.code_at + k] == dst) return false;
+        }
+        return true;
+      };
+      if (isAdd(bo.opcode)) {
+        // move dst -> t2 ; add t2, tmp -> dst   becomes the in-place   add dst, tmp -> dst
+        // (every operator loads all its inputs before it stores; vm_ops.def)
+        const uint64_t dst = src.code[B.code_at + 2];
+        for (int q = 0; q < 2; q++) {
+          const uint64_t t2 = src.code[B.code_at + q], other = src.code[B.code_at + 1 - q];
+          if (t2 == dst || other == dst || other == t2) continue;
+          const uint32_t mi = soleWriter(t2, bi);
+          if (mi == ~0u || mi >= bi || bi - mi > 16 || dropped[mi] || inPort(t2, bytes)) continue;
+          const Inst &M = insts[mi];
+          const OpRef &mo = ops[M.op];
+          if (!isMove(mo.opcode) || mo.lane_width != bo.lane_width || table[mo.opcode].args[0].comps != comps) continue;
+          if (src.code[M.code_at] != dst || src.code[M.code_at + 1] != t2) continue;
+          if (!untouched(mi, ~0u, dst)) continue;
+          code[B.code_at + q] = dst;
+          dropped[mi] = 1;
+          out.n_folded++;
+          break;
+        }
+        continue;
+      }
+      // A -> tmp ; move tmp -> dst   becomes   A -> dst
+      const uint64_t tmp = src.code[B.code_at], dst = src.code[B.code_at + 1];
+      if (tmp == dst) continue;
+      const uint32_t ai = soleWriter(tmp, bi);
+      if (ai == ~0u || ai >= bi || bi - ai > 16 || dropped[ai]) continue;
+      const Inst &A = insts[ai];
+      const OpRef &ao = ops[A.op];
+      const OpSig &asig = table[ao.opcode];
+      if (asig.coop || ao.lane_width != bo.lane_width) continue;
+      bool local = true;
+      for (auto &a : asig.args) local &= (a.kind == ARG_T) || (a.kind == ARG_S && ao.lane_width == 1);
+      if (!local) continue;
+      int k_out = -1;
+      bool dst_used = false;
+      for (size_t k = 0; k < asig.args.size(); k++) {
+        if (code[A.code_at + k] == dst) dst_used = true;  // A reads dst or already writes it
+        if (asig.args[k].is_input) continue;
+        if (src.code[A.code_at + k] == tmp && asig.args[k].comps == comps && asig.args[k].kind == ARG_T) k_out = (int)k;
+      }
+      if (k_out < 0 || dst_used || inPort(tmp, bytes) || !untouched(ai, ~0u, dst)) continue;
+      code[A.code_at + k_out] = dst;
+      dropped[bi] = 1;
+      out.n_folded++;
+    }
+    if (out.n_folded) {
+      size_t w = 0;
+      for (size_t i = 0; i < insts.size(); i++)
+        if (!dropped[i]) insts[w++] = insts[i];
+      insts.resize(w);
+    }
+  }
+
   // ---- 3. levels (ASAP) with RAW / WAR / WAW edges keyed by argument start address
   // an argument is tracked by its start address; block arguments by the start address of every element
   auto forEachKey = [&](const Inst &in, size_t k, const std::function<void(uint64_t)> &f) {
     const ArgSig &a = table[ops[in.op].opcode].args[k];
-    uint64_t addr = src.code[in.code_at + k];
+    uint64_t addr = code[in.code_at + k];
     if (!isBlock(a.kind)) {
       f(addr);
       return;
@@ -227,7 +373,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   for (auto &in : insts) {
     size_t na = table[ops[in.op].opcode].args.size();
     for (size_t k = 0; k < na; k++) {
-      uint64_t a = src.code[in.code_at + k];
+      uint64_t a = code[in.code_at + k];
       if (a % 8) throw std::runtime_error("argument address not 8-byte aligned");
       if (a + src.ops[in.op].args[k].size > src.memory_size)
         throw std::runtime_error("argument address outside the memory image");
@@ -362,7 +508,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       for (size_t k = 0; k < sig.args.size(); k++) {
         if (!sig.args[k].is_input) continue;
         if (arg_wlevel[in.code_at + k] >= P) continue;
-        uint64_t a = src.code[in.code_at + k], e = a + src.ops[in.op].args[k].size - 1;
+        uint64_t a = code[in.code_at + k], e = a + src.ops[in.op].args[k].size - 1;
         for (uint64_t line = a / 128; line <= e / 128; line++) level_lines[in.level].push_back((uint32_t)line);
       }
     }
@@ -496,7 +642,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       for (auto &s : streams) {
         room(s, na + 3);
         s.push_back(HeaderBits::make(o.opcode, false, 1, na, true));
-        for (uint32_t k = 0; k < na; k++) s.push_back((uint32_t)(src.code[in.code_at + k] / 8));
+        for (uint32_t k = 0; k < na; k++) s.push_back((uint32_t)(code[in.code_at + k] / 8));
         s.push_back(imm0);
         s.push_back(imm1);
       }
@@ -566,7 +712,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         const OpSig &sig = table[o.opcode];
         for (size_t k = 0; k < sig.args.size(); k++) {
           if (sig.args[k].is_input) continue;
-          uint64_t addr = src.code[in.code_at + k];
+          uint64_t addr = code[in.code_at + k];
           if (ringEligible(o, sig.args[k])) {
             uint32_t slot = ring.alloc(addr, sig.args[k].comps);
             if (slot != ~0u) out_slot[addr] = slot;
@@ -599,7 +745,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         for (uint32_t i = 0; i < bd.count && !dual; i++) {
           const Inst &in = member(bd, i, p);
           for (uint32_t k = 0; k < na; k++)
-            if (!sig.args[k].is_input && out_slot.count(src.code[in.code_at + k])) dual = true;
+            if (!sig.args[k].is_input && out_slot.count(code[in.code_at + k])) dual = true;
         }
       room(s, 1 + (size_t)na * stride * (dual ? 2 : 1));
       s.push_back(HeaderBits::make(opcode, bd.wide, bd.count, na) | ((dual ? 1u : 0u) << 22));
@@ -608,7 +754,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       for (uint32_t i = 0; i < bd.count; i++) {
         const Inst &in = member(bd, i, p);
         for (uint32_t k = 0; k < na; k++) {
-          uint64_t addr = src.code[in.code_at + k];
+          uint64_t addr = code[in.code_at + k];
           uint32_t image_word = (uint32_t)(addr / 8), word = image_word;
           if (use_gpool && ringEligible(bo, sig.args[k]) && sig.args[k].is_input) {
             auto pc_it = pool_of_const.find(addr);

@@ -26,6 +26,7 @@ static constexpr uint32_t kNoSlot = 0xffffffffu;
 // an operand address is  m + 8 * (word + lane)  plus an immediate per component.
 template <int kAS, int kCS, bool kPlain>
 struct CtxT {
+  static constexpr bool kPlainWords = kPlain;
   double *m;           // base of this tile's memory image (global memory)
   double *ring;        // base of this warp's slot ring (shared memory)
   const uint32_t *a;   // first argument word of this thread's sub-instruction
@@ -48,6 +49,7 @@ struct CtxT {
   TRX_HD const double *GPOOL() const { return kPlain ? nullptr : gpool; }
 };
 using Ctx = CtxT<0, 0, false>;
+using CtxPlain = CtxT<0, 0, true>;  // run-time strides, plain argument words (host emulation of the staged kernel)
 
 template <class C>
 TRX_HD uint32_t argword(const C &c, int k) { return c.preloaded ? c.w[k] : c.a[k * c.AS()]; }

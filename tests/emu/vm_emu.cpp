@@ -61,6 +61,7 @@ int emu_program_create_from_blob(const void *blob, size_t bytes, int warps, emu_
     if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_CHAIN")) opt.chain_cap = (uint32_t)atoi(w);
+    if (const char *w = getenv("TRX_FOLD")) opt.fold_accumulate = atoi(w) != 0;
     trx::lowerProgram(src, opt, p->low);
     bool reverse_only = p->low.has_reverse && !p->low.has_forward;
     p->scalar_inputs = reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED;
@@ -115,6 +116,8 @@ int emu_program_stat(const emu_program *p, const char *key, uint64_t *value) {
   else if (k == "n_ring_only_writes") *value = p->low.n_ring_only_writes;
   else if (k == "n_dual_writes") *value = p->low.n_dual_writes;
   else if (k == "n_image_writes") *value = p->low.n_image_writes;
+  else if (k == "n_folded") *value = p->low.n_folded;
+  else if (k == "n_chained") *value = p->low.n_chained;
   else return fail(TRX_ERR_INVALID, "unknown statistic");
   return TRX_OK;
 }
@@ -225,30 +228,38 @@ int emu_execute(const emu_program *p, emu_memory *m) {
             continue;
           }
           bool dual = (hdr >> 22) & 1u;
+          const bool plain = !low.cta_ring && !low.global_pool && low.ring_doubles == 0;
           for (int lane32 = 0; lane32 < 32; lane32++) {
-            trxvm::Ctx c;
-            c.m = mem;
-            c.ring = low.cta_ring ? rings.data() : rings.data() + (size_t)w * low.ring_doubles;
-            c.nargs = nargs;
-            c.dual = dual;
-            c.rings = true;
-            c.preloaded = false;
-            c.gpool = low.global_pool ? low.pool_values.data() : nullptr;
-            c.rings = !low.global_pool && true;
-            int sub;
-            if (wide) {
-              sub = lane32;
-              c.as = 32;
-              c.cs = 1;
-              c.lo = 0;
+            auto run = [&](auto &c) {
+              c.m = mem;
+              c.ring = low.cta_ring ? rings.data() : rings.data() + (size_t)w * low.ring_doubles;
+              c.nargs = nargs;
+              c.dual = dual;
+              c.preloaded = false;
+              c.gpool = low.global_pool ? low.pool_values.data() : nullptr;
+              c.rings = !low.global_pool;
+              int sub;
+              if (wide) {
+                sub = lane32;
+                c.as = 32;
+                c.cs = 1;
+                c.lo = 0;
+              } else {
+                sub = lane32 >> 3;
+                c.as = 4;
+                c.cs = 8;
+                c.lo = lane32 & 7;
+              }
+              c.a = pc[w] + 1 + sub;
+              if (sub < nsub) trxvm::exec(op, c);
+            };
+            if (plain) {  // the staged kernel's argument-word format (bit 31 of an output = accumulate)
+              trxvm::CtxPlain c;
+              run(c);
             } else {
-              sub = lane32 >> 3;
-              c.as = 4;
-              c.cs = 8;
-              c.lo = lane32 & 7;
+              trxvm::Ctx c;
+              run(c);
             }
-            c.a = pc[w] + 1 + sub;
-            if (sub < nsub) trxvm::exec(op, c);
           }
           pc[w] += 1 + (dual ? 2 * nargs : nargs) * (wide ? 32 : 4);
         }

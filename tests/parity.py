@@ -61,8 +61,9 @@ def tile_arrays(bundle, key):
     return out
 
 
-def check_problem(engine, bundle, n_tiles=None, check_tangent=True):
-    """objective + gradient over several lane tiles: x_prog, x_prep, x_bprop as in solvers/gd.h:50-63"""
+def check_problem(engine, bundle, n_tiles=None, check_tangent=True, compile_bprop=None):
+    """objective + gradient over several lane tiles: x_prog, x_prep, x_bprop as in solvers/gd.h:50-63.
+    compile_bprop: alternative way to lower the adjoint tape (e.g. with accumulate folding)"""
     prog = bundle.view("prog")
     params = tile_arrays(bundle, "params")
     r_ref = tile_arrays(bundle, "r")
@@ -72,7 +73,7 @@ def check_problem(engine, bundle, n_tiles=None, check_tangent=True):
     lanes = 8 * n_tiles
     x_prog = engine.compile(bundle.programs["prog"])
     x_prep = engine.compile(bundle.programs["prep"])
-    x_bprop = engine.compile(bundle.programs["bprop"])
+    x_bprop = (compile_bprop or engine.compile)(bundle.programs["bprop"])
     mem = engine.createMemory(lanes)
     if prog.parameters:
         x_prog.parameterize(trxfile.tiles_to_wide(prog.parameters, params), mem)

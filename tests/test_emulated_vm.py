@@ -27,6 +27,28 @@ def test_dexsyn_rollout(emu_engine, golden, fixture):
     parity.check_problem(emu_engine, golden(fixture))
 
 
+@pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
+@pytest.mark.parametrize("chain", [1, 3])
+def test_accumulate_folding_of_the_adjoint_tape(emu_engine, golden, fixture, chain, monkeypatch):
+    """`rop -> temp; move/add temp -> g` lowered as one record writing g (trx_lower.h, fold_accumulate):
+    same gradient as the reference, fewer records"""
+    bundle = golden(fixture)
+    monkeypatch.setenv("TRX_CHAIN", str(chain))
+    plain = emu_engine.compile(bundle.programs["bprop"])
+
+    def compile_folded(blob):
+        monkeypatch.setenv("TRX_FOLD", "1")
+        try:
+            return emu_engine.compile(blob)
+        finally:
+            monkeypatch.delenv("TRX_FOLD")
+
+    folded = compile_folded(bundle.programs["bprop"])
+    assert folded.stat("n_folded") > 0
+    assert folded.stat("n_bundles") < plain.stat("n_bundles")
+    parity.check_problem(emu_engine, bundle, check_tangent=False, compile_bprop=compile_folded)
+
+
 def test_level_schedule_is_shallower_than_the_tape(emu_engine, golden):
     bundle = golden("dexsyn_small.trxb.xz")
     x = emu_engine.compile(bundle.programs["prog"])
