@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 // ahead of the interpreter.  Header and argument words then cost a shared-memory read instead of two
 // dependent L2 round trips per record; the only global latency left on a record's critical path is its
 // operands.
-template <int kMaxWarps, int kPage, int kPages>
+template <int kMaxWarps, int kPage, int kPages, bool kTrace>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_staged_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
                          uint64_t tile_stride, long long *trace) {
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       asm volatile("cp.async.wait_group %0;" ::"n"(kPages - 1) : "memory");
       __syncwarp();
     }
-    const bool rec_trace = trace && blockIdx.x == 0 && g_rec_trace_flag(trace);
+    const bool rec_trace = kTrace && trace && blockIdx.x == 0 && g_rec_trace_flag(trace);
     long long rt0 = 0, rt1 = 0;
     if (rec_trace) rt0 = clock64();
     const uint32_t *pc = sbuf + (pos & (kRing - 1));
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     if (op == trx::OP_END) break;
     if (op == trx::OP_BARRIER) {
       pos += 1;
-      if (trace && blockIdx.x == 0) {  // development aid: arrival / release clocks per level
+      if (kTrace && trace && blockIdx.x == 0) {  // development aid: arrival / release clocks per level
         long long t0 = clock64();
         int arrived = __syncthreads_count(1);
         long long t1;
@@ -932,11 +932,17 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
       static bool attr_set = false;
       const size_t bytes = (size_t)16 * 512 * kPages * sizeof(uint32_t);
       if (!attr_set) {
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         attr_set = true;
       }
-      trx_vm_staged_kernel<16, 512, kPages><<<(unsigned)m->n_tiles, W * 32, (size_t)W * 512 * kPages * sizeof(uint32_t), stream>>>(
-          p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
+      const size_t smem_bytes = (size_t)W * 512 * kPages * sizeof(uint32_t);
+      if (g_trace)  // development aid (trx_debug_trace): the instrumented instantiation
+        trx_vm_staged_kernel<16, 512, kPages, true><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
+      else
+        trx_vm_staged_kernel<16, 512, kPages, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, nullptr);
     } else {
       if (p->low.global_pool)
         trx_vm_kernel<16, false, true, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(

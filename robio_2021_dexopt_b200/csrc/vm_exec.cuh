@@ -88,9 +88,18 @@ TRX_HD double *slotptr(const C &c, uint32_t w) {
   return (w & kRingFlag) ? (c.ring + (w & 0xffffu)) : (c.m + w);
 }
 template <class C>
-TRX_HD double ld(const C &c, int k, int j) { return slotptr(c, argword(c, k))[j * c.CS() + c.LO()]; }
+TRX_HD double ld(const C &c, int k, int j) {
+  // plain words: slot index + lane in 32 bits (a tile image is < 32 GB), one widening multiply-add to the
+  // address, the component offset as an immediate
+  if (C::kPlainWords) return (c.m + (uint32_t)(argword(c, k) + (uint32_t)c.LO()))[j * c.CS()];
+  return slotptr(c, argword(c, k))[j * c.CS() + c.LO()];
+}
 template <class C>
 TRX_HD void st(const C &c, int k, int j, double v) {
+  if (C::kPlainWords) {
+    (c.m + (uint32_t)(argword(c, k) + (uint32_t)c.LO()))[j * c.CS()] = v;
+    return;
+  }
   slotptr(c, argword(c, k))[j * c.CS() + c.LO()] = v;
   if (c.RINGS() && c.DUAL()) {
     uint32_t w2 = c.preloaded ? c.w2[k] : c.a[(c.nargs + k) * c.AS()];
