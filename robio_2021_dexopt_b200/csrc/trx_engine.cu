@@ -104,8 +104,10 @@ __device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, 
     for (; j < n_out; j++) acc0 = fma(sg[j * 8 + lane], __ldg(Wi + j), acc0);
     gx[o] = (acc0 + acc1) + (acc2 + acc3);
   }
-  // gW[i][j] += sum over lanes of x[i] * gy[j]   (lane sum as reverse_batch, then one accumulate per frame)
-  for (int e = tid; e < n_in * n_out; e += nt) {
+  // gW[i][j] += sum over lanes of x[i] * gy[j]   (lane sum as reverse_batch, then one accumulate per frame).
+  // Four elements per thread and trip: their read-modify-writes are independent, so the four loads of
+  // gW are issued together instead of one L2 round trip per element.
+  auto lanedot = [&](int e) {
     const int i = e / n_out, j = e - i * n_out;
     const double *xi = sx + i * 8, *gj = sg + j * 8;
     double r0 = xi[0] * gj[0], r1 = xi[1] * gj[1];
@@ -115,8 +117,19 @@ __device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, 
     r1 = fma(xi[5], gj[5], r1);
     r0 = fma(xi[6], gj[6], r0);
     r1 = fma(xi[7], gj[7], r1);
-    gW[e] += r0 + r1;
+    return r0 + r1;
+  };
+  const int n_w = n_in * n_out;
+  int e = tid;
+  for (; e + 3 * nt < n_w; e += 4 * nt) {
+    const double w0 = gW[e], w1 = gW[e + nt], w2 = gW[e + 2 * nt], w3 = gW[e + 3 * nt];
+    const double d0 = lanedot(e), d1 = lanedot(e + nt), d2 = lanedot(e + 2 * nt), d3 = lanedot(e + 3 * nt);
+    gW[e] = w0 + d0;
+    gW[e + nt] = w1 + d1;
+    gW[e + 2 * nt] = w2 + d2;
+    gW[e + 3 * nt] = w3 + d3;
   }
+  for (; e < n_w; e += nt) gW[e] += lanedot(e);
   for (int j = tid; j < n_out; j += nt) {
     const double *gj = sg + j * 8;
     gb[j] += ((gj[0] + gj[1]) + (gj[2] + gj[3])) + ((gj[4] + gj[5]) + (gj[6] + gj[7]));

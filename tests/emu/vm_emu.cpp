@@ -121,6 +121,46 @@ int emu_program_stat(const emu_program *p, const char *key, uint64_t *value) {
   else return fail(TRX_ERR_INVALID, "unknown statistic");
   return TRX_OK;
 }
+// walks every warp's stream: each must start on a page boundary, no record may straddle a page, every
+// stream must hold the same number of BARRIER words and end with END
+int emu_program_check_streams(const emu_program *p) {
+  const auto &low = p->low;
+  const uint32_t PG = low.page_words;
+  uint64_t barriers0 = 0;
+  for (uint32_t w = 0; w < low.n_warps; w++) {
+    uint64_t begin = low.stream_begin[w], end = low.stream_begin[w + 1], at = begin, barriers = 0;
+    if (PG && (begin % PG || end % PG)) return fail(TRX_ERR_INVALID, "stream not page aligned");
+    bool ended = false;
+    while (at < end) {
+      uint32_t hdr = low.stream[at], op = hdr & 0x7ffu;
+      uint64_t n = 1;
+      if (op == trx::OP_END) {
+        ended = true;
+        break;
+      } else if (op == trx::OP_BARRIER) {
+        barriers++;
+      } else if (op == trx::OP_PAGE) {
+        if (!PG) return fail(TRX_ERR_INVALID, "page word in an unpaged stream");
+        n = PG - ((at - begin) % PG);
+      } else if (op == trx::OP_PREFETCH) {
+        n = 33;
+      } else {
+        uint32_t nargs = (hdr >> 17) & 15u;
+        bool wide = (hdr >> 11) & 1u, dual = (hdr >> 22) & 1u;
+        n = ((hdr >> 21) & 1u) ? 1 + nargs + 2 : 1 + (uint64_t)(dual ? 2 * nargs : nargs) * (wide ? 32 : 4);
+      }
+      if (PG && op != trx::OP_PAGE && (at - begin) / PG != (at - begin + n - 1) / PG)
+        return fail(TRX_ERR_INVALID, "record straddles a stream page");
+      at += n;
+    }
+    if (!ended) return fail(TRX_ERR_INVALID, "stream without END");
+    if (w == 0) barriers0 = barriers;
+    else if (barriers != barriers0) return fail(TRX_ERR_INVALID, "streams disagree on the number of levels");
+  }
+  if (barriers0 != low.n_levels) return fail(TRX_ERR_INVALID, "barrier count differs from the level count");
+  return TRX_OK;
+}
+
 int emu_memory_create(uint64_t lanes, emu_memory **out) {
   if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
   auto *m = new emu_memory();

@@ -30,6 +30,12 @@ class EmuExecutable:
         if not self._compiled:
             raise RuntimeError("call compile(...) before use")
 
+    def check_streams(self):
+        self._check()
+        self.lib.emu_program_check_streams.argtypes = [ctypes.c_void_p]
+        if self.lib.emu_program_check_streams(self._h) != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+
     def stat(self, key):
         v = ctypes.c_uint64()
         assert self.lib.emu_program_stat(self._h, key.encode(), ctypes.byref(v)) == 0

@@ -49,6 +49,29 @@ def test_accumulate_folding_of_the_adjoint_tape(emu_engine, golden, fixture, cha
     parity.check_problem(emu_engine, bundle, check_tangent=False, compile_bprop=compile_folded)
 
 
+@pytest.mark.parametrize("chain", [1, 2, 4, 8, 64])
+def test_chain_levelisation_keeps_the_numbers(emu_engine, golden, chain, monkeypatch):
+    """instructions appended to their producer's chain (trx_lower.h) run in program order on the same
+    threads: residuals, gradient and tangent stay the reference's for every chain cap, levels shrink"""
+    bundle = golden("dexsyn_small.trxb.xz")
+    monkeypatch.setenv("TRX_CHAIN", "1")
+    flat = emu_engine.compile(bundle.programs["bprop"]).stat("n_levels")
+    monkeypatch.setenv("TRX_CHAIN", str(chain))
+    x = emu_engine.compile(bundle.programs["bprop"])
+    assert (x.stat("n_levels") < flat) if chain > 1 else (x.stat("n_levels") == flat)
+    assert (x.stat("n_chained") > 0) == (chain > 1)
+    parity.check_problem(emu_engine, bundle)
+
+
+@pytest.mark.parametrize("fixture", ["optests_8d.trxb", "fkchain24.trxb", "dexsyn_small.trxb.xz"])
+def test_stream_layout_invariants(emu_engine, golden, fixture):
+    """what the staged kernel relies on: page-aligned per-warp streams, no record across a page boundary,
+    the same number of BARRIER words in every warp's stream"""
+    bundle = golden(fixture)
+    for name, blob in bundle.programs.items():
+        emu_engine.compile(blob).check_streams()
+
+
 def test_level_schedule_is_shallower_than_the_tape(emu_engine, golden):
     bundle = golden("dexsyn_small.trxb.xz")
     x = emu_engine.compile(bundle.programs["prog"])
