@@ -79,14 +79,21 @@ __device__ __forceinline__ void dense_forward_dev(const uint32_t *a, double *m, 
   __syncthreads();  // sx is reused by the next cooperative record
 }
 
-__device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, double *sx, double *sg) {
+__device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, double *sx, double *sg, double *sgT) {
   const double *x = m + a[0], *W = m + a[1];
   double *gx = m + a[4], *gW = m + a[5], *gb = m + a[6];
   const double *gy = m + a[7];
   const int n_in = (int)a[8], n_out = (int)a[9];
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int e = tid; e < n_in * 8; e += nt) sx[e] = x[e];
-  for (int e = tid; e < n_out * 8; e += nt) sg[e] = gy[e];
+  // gy twice: [j][lane] for the gx products (a warp reads the 8 lanes of one j), [lane][j] for the lane sums
+  // of gW and gb (a warp reads consecutive j of one lane) -- either use on the other layout is a 16-way
+  // shared-memory bank conflict
+  for (int e = tid; e < n_out * 8; e += nt) {
+    const double v = gy[e];
+    sg[e] = v;
+    sgT[(e & 7) * n_out + (e >> 3)] = v;
+  }
   __syncthreads();
   // gx[i] = sum_j gy[j] * W[i][j]
   for (int o = tid; o < n_in * 8; o += nt) {
@@ -109,14 +116,14 @@ __device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, 
   // gW are issued together instead of one L2 round trip per element.
   auto lanedot = [&](int e) {
     const int i = e / n_out, j = e - i * n_out;
-    const double *xi = sx + i * 8, *gj = sg + j * 8;
-    double r0 = xi[0] * gj[0], r1 = xi[1] * gj[1];
-    r0 = fma(xi[2], gj[2], r0);
-    r1 = fma(xi[3], gj[3], r1);
-    r0 = fma(xi[4], gj[4], r0);
-    r1 = fma(xi[5], gj[5], r1);
-    r0 = fma(xi[6], gj[6], r0);
-    r1 = fma(xi[7], gj[7], r1);
+    const double *xi = sx + i * 8, *gj = sgT + j;
+    double r0 = xi[0] * gj[0], r1 = xi[1] * gj[n_out];
+    r0 = fma(xi[2], gj[2 * n_out], r0);
+    r1 = fma(xi[3], gj[3 * n_out], r1);
+    r0 = fma(xi[4], gj[4 * n_out], r0);
+    r1 = fma(xi[5], gj[5 * n_out], r1);
+    r0 = fma(xi[6], gj[6 * n_out], r0);
+    r1 = fma(xi[7], gj[7 * n_out], r1);
     return r0 + r1;
   };
   const int n_w = n_in * n_out;
@@ -131,10 +138,157 @@ __device__ __forceinline__ void dense_reverse_dev(const uint32_t *a, double *m, 
   }
   for (; e < n_w; e += nt) gW[e] += lanedot(e);
   for (int j = tid; j < n_out; j += nt) {
+    const double *gj = sgT + j;
+    gb[j] += ((gj[0] + gj[n_out]) + (gj[2 * n_out] + gj[3 * n_out])) +
+             ((gj[4 * n_out] + gj[5 * n_out]) + (gj[6 * n_out] + gj[7 * n_out]));
+  }
+  __syncthreads();
+}
+
+// ---- dense layers on the FP64 tensor cores (DMMA m8n8k4; tcgen05 has no f64 kind) ----------------
+// The 8 rollouts of a tile are the M = 8 rows of every product, so a dense layer is a row of 8x8 output
+// tiles, one warp each.  Fragment layout of mma.sync.m8n8k4.f64 (g = lane >> 2, t = lane & 3):
+//   A (8x4, row)  a    = A[g][t]          B (4x8, col)  b = B[t][g]          C (8x8)  c0,c1 = C[g][2t], C[g][2t+1]
+// Each thread loads 2 operands per 8 multiply-adds instead of 2 per 1.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// One 8x8 output tile: c += A * B over k = 0 .. k_pad (multiple of 4), eight k-steps (32 values of k) per
+// trip so that their operand loads are in flight together, on two accumulator chains.  loadA(k) / loadB(k)
+// return the fragment elements for this thread's k (A from shared memory, B from global memory, zero
+// when out of range).  Kept small on purpose: these functions are inlined into the interpreter and must
+// not push it over its register budget (a 124-register variant with operands prefetched ahead of the
+// staging barrier was measured: no faster, and the spilling one 12 % slower overall).
+template <class FA, class FB>
+__device__ __forceinline__ void mma_tile(double &c0, double &c1, int k_pad, int t, FA loadA, FB loadB) {
+  double d0 = 0.0, d1 = 0.0;
+  for (int k0 = 0; k0 < k_pad; k0 += 32) {
+    double fa[8], fb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const bool on = k0 + 4 * u < k_pad;
+      fb[u] = on ? loadB(k0 + 4 * u + t) : 0.0;
+      fa[u] = on ? loadA(k0 + 4 * u + t) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      if (k0 + 4 * u < k_pad) dmma884(c0, c1, fa[u], fb[u]);
+      if (k0 + 4 * u + 4 < k_pad) dmma884(d0, d1, fa[u + 1], fb[u + 1]);
+    }
+  }
+  c0 += d0;
+  c1 += d1;
+}
+
+// y[j][lane] = sum_i x[i][lane] W[i][j] + b[j]      (neural.h:176-181, tensor.h:147-159)
+__device__ __forceinline__ void dense_forward_mma(const uint32_t *a, double *m, double *sx) {
+  const double *x = m + a[0], *W = m + a[1], *b = m + a[2];
+  double *y = m + a[3];
+  const int n_in = (int)a[4], n_out = (int)a[5];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int k_pad = (n_in + 3) & ~3;
+  for (int e = tid; e < k_pad * 8; e += nt) sx[e] = (e < n_in * 8) ? x[e] : 0.0;
+  __syncthreads();
+  const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int tile = tid >> 5; tile * 8 < n_out; tile += nt >> 5) {
+    const int n = tile * 8 + g;  // output column this thread feeds as B operand
+    const double *Wn = W + n;
+    double c0 = 0.0, c1 = 0.0;
+    mma_tile(
+        c0, c1, k_pad, t, [&](int k) { return sx[k * 8 + g]; },
+        [&](int k) { return (k < n_in && n < n_out) ? __ldg(Wn + (size_t)k * n_out) : 0.0; });
+    const int j = tile * 8 + 2 * t;
+    if (j < n_out) y[j * 8 + g] = c0 + __ldg(b + j);
+    if (j + 1 < n_out) y[(j + 1) * 8 + g] = c1 + __ldg(b + j + 1);
+  }
+  __syncthreads();  // sx is reused by the next cooperative record
+}
+
+// gx[i][lane] = sum_j gy[j][lane] W[i][j];  gW[i][j] += sum_lanes x[i] gy[j];  gb[j] += sum_lanes gy[j]
+// clk (development aid, tracing instantiation only): per-phase clock sums of tile 0
+__device__ __forceinline__ void dense_reverse_mma(const uint32_t *a, double *m, double *sx, double *sg, long long *clk = nullptr) {
+  long long tc[6];
+  if (clk) tc[0] = tc[1] = clock64();
+  const double *x = m + a[0], *W = m + a[1];
+  double *gx = m + a[4], *gW = m + a[5], *gb = m + a[6];
+  const double *gy = m + a[7];
+  const int n_in = (int)a[8], n_out = (int)a[9];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int in_pad = (n_in + 7) & ~7, out_pad = (n_out + 7) & ~7;
+  for (int e = tid; e < in_pad * 8; e += nt) sx[e] = (e < n_in * 8) ? x[e] : 0.0;
+  for (int e = tid; e < out_pad * 8; e += nt) sg[e] = (e < n_out * 8) ? gy[e] : 0.0;
+  __syncthreads();
+  if (clk) tc[2] = clock64();
+  const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int warp = tid >> 5, n_warps = nt >> 5;
+  const int tiles_in = in_pad >> 3, tiles_out = out_pad >> 3;
+  // gx: rows = rollouts, columns = i, k = j.   A[g][t] = gy[k0+t][g],  B[t][g] = W[i0+g][k0+t]
+  for (int tile = warp; tile < tiles_in; tile += n_warps) {
+    const int i = tile * 8 + g;
+    const double *Wi = W + (size_t)i * n_out;
+    double c0 = 0.0, c1 = 0.0;
+    mma_tile(
+        c0, c1, out_pad, t, [&](int k) { return sg[k * 8 + g]; },
+        [&](int k) { return (k < n_out && i < n_in) ? __ldg(Wi + k) : 0.0; });
+    const int i0 = tile * 8 + 2 * t;
+    if (i0 < n_in) gx[i0 * 8 + g] = c0;
+    if (i0 + 1 < n_in) gx[(i0 + 1) * 8 + g] = c1;
+  }
+  if (clk) tc[3] = clock64();
+  // gW: rows = i, columns = j, k = rollout lane.   A[g][t] = x[i0+g][l0+t],  B[t][g] = gy[j0+g][l0+t]
+  // The accumulator starts from what the earlier frames left in gW.  Tiles (ti, tj) are walked without a
+  // division per tile; two tiles per trip so that their read-modify-writes overlap.
+  {
+    int ti = warp / tiles_out, tj = warp - ti * tiles_out;
+    const int step_i = n_warps / tiles_out, step_j = n_warps - step_i * tiles_out;
+    auto advance = [&](int &vi, int &vj) {
+      vi += step_i;
+      vj += step_j;
+      if (vj >= tiles_out) {
+        vj -= tiles_out;
+        vi++;
+      }
+    };
+    while (ti < tiles_in) {
+      int ui = ti, uj = tj;
+      advance(ui, uj);
+      const bool second = ui < tiles_in;
+      const int i_a = ti * 8 + g, j_a = tj * 8 + 2 * t, i_b = ui * 8 + g, j_b = uj * 8 + 2 * t;
+      double *pa = gW + (size_t)i_a * n_out + j_a, *pb = gW + (size_t)i_b * n_out + j_b;
+      const bool a0 = i_a < n_in && j_a < n_out, a1 = i_a < n_in && j_a + 1 < n_out;
+      const bool b0 = second && i_b < n_in && j_b < n_out, b1 = second && i_b < n_in && j_b + 1 < n_out;
+      double ca0 = a0 ? pa[0] : 0.0, ca1 = a1 ? pa[1] : 0.0, cb0 = b0 ? pb[0] : 0.0, cb1 = b1 ? pb[1] : 0.0;
+      const double *xa = sx + i_a * 8 + t, *ga = sg + (tj * 8 + g) * 8 + t;
+      dmma884(ca0, ca1, xa[0], ga[0]);
+      dmma884(ca0, ca1, xa[4], ga[4]);
+      if (second) {
+        const double *xb = sx + i_b * 8 + t, *gb2 = sg + (uj * 8 + g) * 8 + t;
+        dmma884(cb0, cb1, xb[0], gb2[0]);
+        dmma884(cb0, cb1, xb[4], gb2[4]);
+      }
+      if (a0) pa[0] = ca0;
+      if (a1) pa[1] = ca1;
+      if (b0) pb[0] = cb0;
+      if (b1) pb[1] = cb1;
+      ti = ui;
+      tj = uj;
+      if (second) advance(ti, tj);
+    }
+  }
+  if (clk) tc[4] = clock64();
+  for (int j = tid; j < n_out; j += nt) {
     const double *gj = sg + j * 8;
     gb[j] += ((gj[0] + gj[1]) + (gj[2] + gj[3])) + ((gj[4] + gj[5]) + (gj[6] + gj[7]));
   }
   __syncthreads();
+  if (clk && tid == 0) {
+    tc[5] = clock64();
+    for (int p = 0; p < 5; p++) clk[p] += tc[p + 1] - tc[p];
+    clk[7] += 1;
+  }
 }
 
 __device__ __forceinline__ bool g_rec_trace_flag(const long long *trace) { return trace[(1ll << 20) - 1] != 0; }
@@ -149,7 +303,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                   uint64_t tile_stride, uint32_t ring_doubles, long long *trace, const double *__restrict__ pool,
                   uint32_t pool_offset, uint32_t pool_doubles, uint32_t page_words) {
   extern __shared__ double trx_rings[];
-  __shared__ double dense_x[128 * 8], dense_g[128 * 8];  // staged operand blocks of the dense operators
+  __shared__ double dense_x[128 * 8], dense_g[128 * 8], dense_gT[128 * 8];  // staged operand blocks of the dense operators
   uint32_t trace_level = 0, rec_count = 0;
   double *m = mem + (uint64_t)blockIdx.x * tile_stride;
   const int warp = threadIdx.x >> 5;
@@ -218,7 +372,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       if (op == trx::OP_X_DENSE && n0 <= 128)
         dense_forward_dev(pc + 1, m, dense_x);
       else if (op == trx::OP_R_X_DENSE && n0 <= 128 && n1 <= 128)
-        dense_reverse_dev(pc + 1, m, dense_x, dense_g);
+        dense_reverse_dev(pc + 1, m, dense_x, dense_g, dense_gT);
       else
         trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
       pc = next;
@@ -371,9 +525,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       // block-cooperative record: every warp holds it at the same stream position
       const uint32_t n0 = pc[1 + nargs], n1 = pc[2 + nargs];
       if (op == trx::OP_X_DENSE && n0 <= 128)
-        dense_forward_dev(pc + 1, m, dense_x);
+        dense_forward_mma(pc + 1, m, dense_x);
       else if (op == trx::OP_R_X_DENSE && n0 <= 128 && n1 <= 128)
-        dense_reverse_dev(pc + 1, m, dense_x, dense_g);
+        dense_reverse_mma(pc + 1, m, dense_x, dense_g,
+                          (kTrace && trace && blockIdx.x == 0) ? trace + (1ll << 20) + 16 * 4096 * 4 : nullptr);
       else
         trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
       pos += 1 + nargs + 2;

@@ -162,7 +162,7 @@ TRX_HD void stt(const C &c, int k, int o, const TwistV &t) {
 }
 
 // number of arguments in a signature string (tokens separated by single blanks)
-constexpr int sigArgCount(const char *sig) {
+TRX_HD constexpr int sigArgCount(const char *sig) {
   int n = 0;
   bool in_token = false;
   for (const char *p = sig; *p; p++) {

@@ -39,6 +39,11 @@ t = buf.cpu().numpy().reshape(nlev, W, 2)
 recbuf = torch.empty(16 * 4096 * 4, dtype=torch.int64, device="cuda")
 ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(recbuf.data_ptr()), ctypes.c_void_p(ptr.value + (1 << 20) * 8), ctypes.c_size_t(16 * 4096 * 32), 3)
 rec = recbuf.cpu().numpy().reshape(16, 4096, 4)
+dclk = torch.empty(8, dtype=torch.int64, device='cuda')
+ctypes.CDLL('libcudart.so').cudaMemcpy(ctypes.c_void_p(dclk.data_ptr()), ctypes.c_void_p(ptr.value + ((1 << 20) + 16 * 4096 * 4) * 8), ctypes.c_size_t(64), 3)
+dclk = dclk.cpu().numpy()
+print('raw dense clocks', dclk.tolist())
+if dclk[7]: print('dense reverse, mean clocks per phase {preload issue, stage+barrier, gx, gW, gb+barrier}:', (dclk[:5] / dclk[7]).round(0).tolist(), 'calls', int(dclk[7]))
 L.trx_debug_trace(0, None)
 valid = rec[:, :, 0] > 0
 args_t = (rec[:, :, 1] - rec[:, :, 0])[valid]
