@@ -204,6 +204,13 @@ trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint
 trx_status trx_objective_evaluate(trx_objective *o, const double *x, double *loss, double *gradient, void *stream);
 /* device buffers: d_x[n_x] in, d_out[1 + n_x] = {loss, gradient} out; asynchronous on `stream` */
 trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, double *d_out, void *stream);
+/* GradientDescentSolver::_step (tractor/include/tractor/solvers/gd.h:43-129) n_steps times without leaving
+ * the device: engine work as trx_objective_evaluate_device, then v <- momentum v - learning_rate g ; x <- x + v
+ * (gd.h:74,96; skipped when a gradient element is not finite, gd.h:72,124-126).  d_x[n_x] in/out,
+ * d_v[n_x] in/out (zero it for a fresh solver), d_losses[n_steps] out or NULL: the loss before each update
+ * (what Solver::loss() returns after step(), solver.cpp:96-103).  Asynchronous on `stream`. */
+trx_status trx_objective_gd_steps(trx_objective *o, double *d_x, double *d_v, double learning_rate, double momentum,
+                                  uint32_t n_steps, double *d_losses, void *stream);
 /* CUDA-event times of the last trx_objective_evaluate: {h2d, kernels, d2h} in milliseconds */
 trx_status trx_objective_last_times(const trx_objective *o, float *ms3);
 /* per-program kernel timing with CUDA events on the launching stream: enable, then call

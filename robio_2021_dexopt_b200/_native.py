@@ -61,6 +61,8 @@ def lib() -> ctypes.CDLL:
     L.trx_objective_parameterize.argtypes = [c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
     L.trx_objective_evaluate.argtypes = [c.c_void_p, c.c_void_p, c.POINTER(c.c_double), c.c_void_p, c.c_void_p]
     L.trx_objective_evaluate_device.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    L.trx_objective_gd_steps.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_double, c.c_double, c.c_uint32,
+                                         c.c_void_p, c.c_void_p]
     L.trx_objective_last_times.argtypes = [c.c_void_p, c.POINTER(c.c_float)]
     L.trx_objective_set_profiling.argtypes = [c.c_void_p, c.c_int]
     L.trx_objective_profile_collect.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]

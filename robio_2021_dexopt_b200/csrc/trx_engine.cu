@@ -698,6 +698,24 @@ __global__ void trx_loss_kernel(const double *__restrict__ partial, uint32_t n, 
   if (threadIdx.x == 0) out[0] = red[0];
 }
 
+// GradientDescentSolver::_step after the engine work (solvers/gd.h:64-129): v <- mu v - lr g ; x <- x + v,
+// skipped altogether when any gradient element is not finite (gd.h:72,124-126).  One CTA: the optimisation
+// vector is the policy's few thousand weights.  out = {loss, g[n]} of trx_objective_evaluate_device.
+__global__ void trx_gd_update_kernel(double *x, double *v, const double *out, uint32_t n, double lr, double mu,
+                                     double *loss_log) {
+  const double *g = out + 1;
+  int finite = 1;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) finite &= isfinite(g[i]) ? 1 : 0;
+  finite = __syncthreads_and(finite);
+  if (threadIdx.x == 0 && loss_log) *loss_log = out[0];
+  if (!finite) return;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double vi = mu * v[i] - lr * g[i];
+    v[i] = vi;
+    x[i] = x[i] + vi;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ objects
@@ -1482,6 +1500,25 @@ trx_status trx_objective_profile_collect(trx_objective *o, double *ms3, uint64_t
   o->prof_count++;
   for (int k = 0; k < 3; k++) ms3[k] = o->prof_ms[k];
   if (evaluations) *evaluations = o->prof_count;
+  return TRX_OK;
+}
+
+// n_steps gradient-descent steps entirely on the device: no host round trip between the steps.
+// d_x[n_x] (in/out) optimisation variables, d_v[n_x] (in/out) momentum state, d_losses[n_steps] (out, may be
+// null) the loss BEFORE each update, as GradientDescentSolver::loss() reports it.  Asynchronous on `stream`.
+trx_status trx_objective_gd_steps(trx_objective *o, double *d_x, double *d_v, double learning_rate, double momentum,
+                                  uint32_t n_steps, double *d_losses, void *stream_) {
+  if (!o || !d_x || !d_v) return fail(TRX_ERR_INVALID, "bad argument");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  for (uint32_t it = 0; it < n_steps; it++) {
+    trx_status s = trx_objective_evaluate_device(o, d_x, o->d_out, stream_);
+    if (s != TRX_OK) return s;
+    trx_gd_update_kernel<<<1, 1024, 0, stream>>>(d_x, d_v, o->d_out, (uint32_t)o->n_x, learning_rate, momentum,
+                                                d_losses ? d_losses + it : nullptr);
+    g_launches++;
+  }
+  TRX_CUDA(cudaGetLastError());
   return TRX_OK;
 }
 

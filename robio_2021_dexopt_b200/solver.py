@@ -63,6 +63,14 @@ class Objective:
         check(_native.lib().trx_objective_evaluate_device(self._h, ctypes.c_void_p(d_x_ptr),
                                                           ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
 
+    def gd_steps(self, d_x_ptr: int, d_v_ptr: int, learning_rate: float, momentum: float, n_steps: int,
+                 d_losses_ptr: int = 0, stream: int = 0) -> None:
+        """n_steps GradientDescentSolver steps on the device (no host round trip between them)"""
+        check(_native.lib().trx_objective_gd_steps(self._h, ctypes.c_void_p(d_x_ptr), ctypes.c_void_p(d_v_ptr),
+                                                   ctypes.c_double(learning_rate), ctypes.c_double(momentum),
+                                                   ctypes.c_uint32(n_steps), ctypes.c_void_p(d_losses_ptr),
+                                                   ctypes.c_void_p(stream)))
+
     def set_profiling(self, enable: bool) -> None:
         check(_native.lib().trx_objective_set_profiling(self._h, 1 if enable else 0))
 
@@ -109,6 +117,24 @@ class GradientDescentSolver:
             self.v = self.momentum * self.v - self.learning_rate * g
             self.x = self.x + self.v  # accu program for scalar inputs: plain add (gradients.cpp:396-403)
         return loss
+
+    def steps_on_device(self, n_steps: int) -> np.ndarray:
+        """n_steps steps with x, the momentum state and the update rule resident on the GPU
+        (trx_objective_gd_steps): one upload of x, one download of {x, losses}.  Returns the losses."""
+        import torch
+        dev = torch.device("cuda", self.objective.engine.device)
+        d_x = torch.from_numpy(self.x).to(dev)
+        d_v = torch.from_numpy(self.v).to(dev)
+        d_losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.objective.gd_steps(d_x.data_ptr(), d_v.data_ptr(), self.learning_rate, self.momentum, n_steps,
+                                d_losses.data_ptr(), stream)
+        self.x = d_x.cpu().numpy()
+        self.v = d_v.cpu().numpy()
+        losses = d_losses.cpu().numpy()[:n_steps]
+        if n_steps:
+            self._loss = float(losses[-1])
+        return losses
 
     def loss(self) -> float:  # gd.h:40-41
         return self._loss

@@ -175,6 +175,43 @@ def test_gradient_descent_iterates_match_reference(cuda_engine, golden, fixture)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("momentum", [0.0, 0.5])
+def test_gradient_descent_steps_resident_on_the_device(cuda_engine, golden, momentum):
+    """trx_objective_gd_steps (x, momentum state and update on the GPU, no host round trip) against the
+    host-side loop over trx_objective_evaluate; with momentum 0 also against the reference's iterates"""
+    import numpy as np
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    bundle = golden("dexsyn_small.trxb.xz")
+    lr = float(bundle.arrays["gd/learning_rate"][0])
+
+    def make():
+        obj = pkg.Objective(cuda_engine, bundle, lanes=16)
+        obj.parameterize(trxfile.tiles_to_wide(bundle.view("prog").parameters, parity.tile_arrays(bundle, "params")))
+        solver = pkg.GradientDescentSolver(obj, learning_rate=lr, momentum=momentum)
+        solver.gather(bundle.arrays["x"])
+        return solver
+
+    host, dev = make(), make()
+    host_losses = [host.step() for _ in range(10)]
+    dev_losses = dev.steps_on_device(4)
+    dev_losses = np.concatenate([dev_losses, dev.steps_on_device(6)])  # the momentum state carries over
+    parity.assert_close(dev_losses, np.array(host_losses), "losses", rtol=1e-12)
+    parity.assert_close(dev.scatter(), host.scatter(), "x after 10 steps", rtol=1e-12)
+    assert dev.loss() == dev_losses[-1]
+    if momentum == 0.0:
+        fresh = make()
+        it = iter(range(10))
+
+        def step():
+            next(it)
+            losses = fresh.steps_on_device(1)
+            return float(losses[0]), fresh.scatter()
+
+        parity.check_gd_iterates(step, bundle)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fuse_dense", [0, 1])
 def test_product_built_problem_on_gpu(cuda_engine, golden, fuse_dense):
     """the product's own recorder + gradients + CUDA engine, end to end, against reference numbers;
