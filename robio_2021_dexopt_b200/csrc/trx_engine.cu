@@ -32,6 +32,7 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 
 // development knob: TRX_STAGED=0 runs generic executables on the kernel that reads its stream from global memory
+constexpr int kStagedWarps = 20;  // warps per tile of the staged kernel
 bool staged_streams() {
   static int v = getenv("TRX_STAGED") ? atoi(getenv("TRX_STAGED")) : 1;
   return v != 0;
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         dense_forward_mma(pc + 1, m, dense_x);
       else if (op == trx::OP_R_X_DENSE && n0 <= 128 && n1 <= 128)
         dense_reverse_mma(pc + 1, m, dense_x, dense_g,
-                          (kTrace && trace && blockIdx.x == 0) ? trace + (1ll << 20) + 16 * 4096 * 4 : nullptr);
+                          (kTrace && trace && blockIdx.x == 0) ? trace + (1ll << 20) + 32 * 4096 * 4 : nullptr);
       else
         trxvm::exec_coop(op, pc + 1, m, (int)threadIdx.x, (int)blockDim.x);
       pos += 1 + nargs + 2;
@@ -889,11 +890,16 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
   p->device = device;
   try {
     trx::LowerOptions opt;
-    if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_PREFETCH")) opt.prefetch_distance = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_CACHE_SLOTS")) opt.ring_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_POOL_SLOTS")) opt.pool_slots = (uint32_t)atoi(w);
     if (const char *w = getenv("TRX_CHAIN")) opt.chain_cap = (uint32_t)atoi(w);
+    // the staged kernel runs 20 warps per tile (640 threads x <= 96 registers fill the register file,
+    // 20 x 8 KB of stream pages + 16 KB of dense staging fit shared memory); the other kernels 16
+    const bool staged = staged_streams() && opt.ring_slots == 0 && opt.pool_slots == 0 && opt.page_words == 512;
+    opt.n_warps = staged ? kStagedWarps : 16;
+    if (const char *w = getenv("TRX_WARPS")) opt.n_warps = (uint32_t)atoi(w);
+    if (opt.n_warps > (staged ? (uint32_t)kStagedWarps : 16u)) return fail(TRX_ERR_INVALID, "TRX_WARPS too large for this kernel");
     // folding needs the plain argument-word format of the staged kernel
     static int fold_env = getenv("TRX_FOLD") ? atoi(getenv("TRX_FOLD")) : 1;
     opt.fold_accumulate = fold_accumulate && fold_env && staged_streams() && opt.ring_slots == 0 && opt.pool_slots == 0 &&
@@ -1116,18 +1122,18 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
       // the product path: stream pages staged in shared memory
       constexpr int kPages = 4;
       static bool attr_set = false;
-      const size_t bytes = (size_t)16 * 512 * kPages * sizeof(uint32_t);
+      const size_t bytes = (size_t)kStagedWarps * 512 * kPages * sizeof(uint32_t);
       if (!attr_set) {
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<16, 512, kPages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         attr_set = true;
       }
       const size_t smem_bytes = (size_t)W * 512 * kPages * sizeof(uint32_t);
       if (g_trace)  // development aid (trx_debug_trace): the instrumented instantiation
-        trx_vm_staged_kernel<16, 512, kPages, true><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+        trx_vm_staged_kernel<kStagedWarps, 512, kPages, true><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
       else
-        trx_vm_staged_kernel<16, 512, kPages, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+        trx_vm_staged_kernel<kStagedWarps, 512, kPages, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, nullptr);
     } else {
       if (p->low.global_pool)

@@ -147,7 +147,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   out = LoweredProgram();
   out.memory_size = (src.memory_size + 255) / 256 * 256;
   out.n_warps = opt.n_warps;
-  if (opt.n_warps < 1 || opt.n_warps > 16) throw std::runtime_error("n_warps out of range (1..16)");
+  if (opt.n_warps < 1 || opt.n_warps > 20) throw std::runtime_error("n_warps out of range (1..20)");
   if (src.memory_size / 8 >= 0xffffffffull) throw std::runtime_error("memory image too large for 32-bit slot indices");
 
   // ---- 1. operator table -> opcodes, signature check

@@ -25,7 +25,7 @@ for it in range(2):
     r = xs["prog"].run(b.arrays["x"], mem); xs["prep"].execute(mem); g = xs["bprop"].run(r, mem)
 nlev = xs[which].stat("n_levels"); W = xs[which].stat("n_warps")
 ptr = ctypes.c_void_p()
-NW = (1 << 20) + 16 * 4096 * 4 + 64
+NW = (1 << 20) + 32 * 4096 * 4 + 64
 assert nlev * W * 2 < (1 << 20) - 1
 L.trx_debug_trace(NW, ctypes.byref(ptr))
 flag = torch.ones(1, dtype=torch.int64, device='cuda')
@@ -36,11 +36,11 @@ torch.cuda.synchronize()
 buf = torch.empty(nlev * W * 2, dtype=torch.int64, device="cuda")
 ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(buf.data_ptr()), ptr, ctypes.c_size_t(nlev * W * 16), 3)
 t = buf.cpu().numpy().reshape(nlev, W, 2)
-recbuf = torch.empty(16 * 4096 * 4, dtype=torch.int64, device="cuda")
-ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(recbuf.data_ptr()), ctypes.c_void_p(ptr.value + (1 << 20) * 8), ctypes.c_size_t(16 * 4096 * 32), 3)
-rec = recbuf.cpu().numpy().reshape(16, 4096, 4)
+recbuf = torch.empty(32 * 4096 * 4, dtype=torch.int64, device="cuda")
+ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(recbuf.data_ptr()), ctypes.c_void_p(ptr.value + (1 << 20) * 8), ctypes.c_size_t(32 * 4096 * 32), 3)
+rec = recbuf.cpu().numpy().reshape(32, 4096, 4)
 dclk = torch.empty(8, dtype=torch.int64, device='cuda')
-ctypes.CDLL('libcudart.so').cudaMemcpy(ctypes.c_void_p(dclk.data_ptr()), ctypes.c_void_p(ptr.value + ((1 << 20) + 16 * 4096 * 4) * 8), ctypes.c_size_t(64), 3)
+ctypes.CDLL('libcudart.so').cudaMemcpy(ctypes.c_void_p(dclk.data_ptr()), ctypes.c_void_p(ptr.value + ((1 << 20) + 32 * 4096 * 4) * 8), ctypes.c_size_t(64), 3)
 dclk = dclk.cpu().numpy()
 print('raw dense clocks', dclk.tolist())
 if dclk[7]: print('dense reverse, mean clocks per phase {preload issue, stage+barrier, gx, gW, gb+barrier}:', (dclk[:5] / dclk[7]).round(0).tolist(), 'calls', int(dclk[7]))
