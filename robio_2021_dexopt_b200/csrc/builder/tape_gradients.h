@@ -58,7 +58,7 @@ inline void packOffsets(std::vector<trxfile::Port> &ports) {
   }
 }
 
-// want_tangent = false skips fprop / hprop (block operators have no forward-mode variant yet)
+// want_tangent = false skips fprop / hprop
 inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, bool want_tangent = true) {
   auto insts = decode(src);
   out = GradientPrograms();
@@ -265,7 +265,21 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, b
       const auto &in = insts[i];
       std::string fname = variantName(src.ops[in.op].name, "forward");
       if (!hasOp(fname)) throw std::runtime_error("variant not found: forward " + src.ops[in.op].name);
-      uint32_t id = internOp(fprop, index, fname);
+      uint32_t id;
+      {
+        uint16_t fopcode;
+        uint32_t flw;
+        trx::findOp(fname, fopcode, flw);
+        if (trx::opTable()[fopcode].coop) {
+          // block operator: argument sizes come from the instruction's own blocks (values, then tangents)
+          std::vector<uint32_t> sizes;
+          for (int rep = 0; rep < 2; rep++)
+            for (uint32_t k = 0; k < in.n_args; k++) sizes.push_back(src.ops[in.op].args[k].size);
+          id = internBlockOp(fprop, index, fname, sizes);
+        } else {
+          id = internOp(fprop, index, fname);
+        }
+      }
       fprop.code.push_back(id);
       size_t n0 = fprop.code.size();
       if (prep_at[i] < 0) {

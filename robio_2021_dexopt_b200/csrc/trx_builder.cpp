@@ -72,7 +72,7 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     uint64_t recorded = b.prog.n_instructions;
     b.finish();
     trxb::GradientPrograms g;
-    std::string want = "," + getS("programs", b.fuse_dense ? "prog,prep,bprop,accu" : "prog,prep,fprop,bprop,hprop,accu") + ",";
+    std::string want = "," + getS("programs", "prog,prep,fprop,bprop,hprop,accu") + ",";
     bool want_tangent = want.find(",fprop,") != std::string::npos || want.find(",hprop,") != std::string::npos;
     trxb::buildGradients(b.prog, g, want_tangent);
 

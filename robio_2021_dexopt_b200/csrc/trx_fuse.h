@@ -382,7 +382,7 @@ inline void lowerFused(const trxfile::Program &src, const std::unordered_set<uin
         const OpSig &sig = table[o.opcode];
         const auto &d = src.ops[in.op];
         uint32_t imm0 = 0, imm1 = 0;
-        if (o.opcode == OP_X_DENSE || o.opcode == OP_R_X_DENSE) {
+        if (o.opcode == OP_X_DENSE || o.opcode == OP_R_X_DENSE || o.opcode == OP_F_X_DENSE) {
           imm0 = d.args[0].size / 64;
           imm1 = d.args[3].size / 64;
           if (d.args[1].size != (uint64_t)imm0 * imm1 * 8 || d.args[2].size != imm1 * 8)

@@ -240,6 +240,19 @@ TRX_HD void exec_coop(uint32_t opcode, const uint32_t *a, double *m, int tid, in
         gb[j] += rs;
       }
     } break;
+    case trx::OP_F_X_DENSE: {
+      // tangent of a dense layer: dy = dx W + x dW + db
+      const double *x = m + a[0], *W = m + a[1];
+      const double *dx = m + a[4], *dW = m + a[5], *db = m + a[6];
+      double *dy = m + a[7];
+      const int n_in = (int)a[8], n_out = (int)a[9];
+      for (int o = tid; o < n_out * 8; o += nthreads) {
+        const int j = o >> 3, lane = o & 7;
+        double acc = 0.0;
+        for (int i = 0; i < n_in; i++) acc += dx[i * 8 + lane] * W[i * n_out + j] + x[i * 8 + lane] * dW[i * n_out + j];
+        dy[j * 8 + lane] = acc + db[j];
+      }
+    } break;
     case trx::OP_X_ZERO_BLOCK: {
       double *z = m + a[0];
       const int n = (int)a[1];

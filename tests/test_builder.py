@@ -56,7 +56,9 @@ def test_built_programs_reproduce_reference_numbers(emu_engine, golden, fixture,
     mine = pkg.build_dexsyn(fuse_dense=fuse_dense, **options)
     for k, v in ref.arrays.items():
         mine.arrays.setdefault(k, v)
-    parity.check_problem(emu_engine, mine, check_tangent=not fuse_dense)
+    parity.check_problem(emu_engine, mine, check_tangent=True)  # fused tapes: forward_x_dense block operator
     if fuse_dense:
         n_ref = int(ref.meta()["n_prog_instructions"])
         assert int(mine.meta()["n_prog_instructions"]) < 0.7 * n_ref
+        assert any(o.name == "forward_x_dense_8d" for o in mine.view("fprop").ops)
+        assert any(o.name == "forward_x_dense_8d" for o in mine.view("hprop").ops)

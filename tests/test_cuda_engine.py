@@ -37,7 +37,7 @@ def test_operator_vocabulary_matches_reference_registry():
     for i in range(L.trx_op_count()):
         name = L.trx_op_name(i).decode()
         sig = L.trx_op_signature(i).decode().split()
-        if name.replace("reverse_", "").startswith("x_"):
+        if name.replace("reverse_", "").replace("forward_", "").startswith("x_"):
             continue  # product extensions (block operators), not reference operators
         for suffix, lanes in (("_8d", 8), ("_d", 1)):
             full = name + suffix
@@ -226,6 +226,10 @@ def test_product_built_problem_on_gpu(cuda_engine, golden, fuse_dense):
     want = float(ref.arrays["loss_total"][0])
     assert abs(loss - want) <= 1e-11 * abs(want)
     parity.assert_close(g, ref.arrays["g_total"], "gradient")
+    # the same tapes as stand-alone executables, including the tangent sweep (forward_x_dense when fused)
+    for k, v in ref.arrays.items():
+        mine.arrays.setdefault(k, v)
+    parity.check_problem(cuda_engine, mine, check_tangent=True)
 
 
 @pytest.mark.gpu
