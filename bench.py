@@ -299,6 +299,7 @@ def main():
         },
         "loss": loss,
         "lowering_stats": {k: {q: obj.info("%s.%s" % (k, q)) for q in ("n_instructions", "n_levels", "n_bundles", "stream_words", "n_ring_reads", "n_image_reads", "n_ring_only_writes", "n_dual_writes", "n_image_writes", "n_prefetch_lines", "n_chained", "n_folded")} for k in ("prog", "prep", "bprop")},
+        "direct_operands": {k: obj.info("direct." + k) for k in ("n_prepare_dropped", "n_arguments_redirected", "n_mul_rewritten")},
         "setup_s": t_build,
         "chunks": n_chunks,
         "device_bytes": obj.info("device_bytes"),

@@ -23,6 +23,7 @@
 #include "../../include/trx_b200.h"
 #include "trx_lower.h"
 #include "trx_fuse.h"
+#include "trx_direct.h"
 #include "vm_exec.cuh"
 
 namespace {
@@ -1215,6 +1216,7 @@ struct trx_objective {
   uint64_t n_x = 0;
   trx_memory *mem = nullptr;
   double *d_x = nullptr, *d_params = nullptr, *d_out = nullptr, *d_partial = nullptr;
+  trx::DirectStats direct;
   double *h_x = nullptr, *h_out = nullptr;  // pinned
   uint64_t param_elems = 0;
   SeedElem *d_seed = nullptr;
@@ -1263,6 +1265,9 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       trxfile::decodeProgram(prog_blob, prog_bytes, p_prog);
       trxfile::decodeProgram(prep_blob, prep_bytes, p_prep);
       trxfile::decodeProgram(bprop_blob, bprop_bytes, p_bprop);
+      // the adjoint reads forward operands in place instead of through x_prep's copies (trx_direct.h)
+      static int direct_env = getenv("TRX_DIRECT") ? atoi(getenv("TRX_DIRECT")) : 1;
+      if (direct_env && !o->fused) trx::directPrepare(p_prep, p_bprop, o->direct);
     } catch (const std::exception &e) {
       return fail(TRX_ERR_INVALID, e.what());
     }
@@ -1374,6 +1379,9 @@ trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t 
   else if (k == "parameter_bytes") *value = o->param_elems * 8;
   else if (k == "device_bytes") *value = o->mem->tile_stride * o->mem->n_tiles * 8;
   else if (k == "fused") *value = o->fused ? 1 : 0;
+  else if (k == "direct.n_prepare_dropped") *value = o->direct.n_prepare_dropped;
+  else if (k == "direct.n_arguments_redirected") *value = o->direct.n_arguments_redirected;
+  else if (k == "direct.n_mul_rewritten") *value = o->direct.n_mul_rewritten;
   else if (k.rfind("prog.", 0) == 0) return trx_program_stat(o->prog, key + 5, value);
   else if (k.rfind("prep.", 0) == 0) {
     if (!o->prep) { *value = 0; return TRX_OK; }

@@ -8,6 +8,7 @@
 // reference's golden vectors without a GPU.  It is NOT part of the product:
 // nothing in robio_2021_dexopt_b200/ loads it, libtrx_b200.so has no CPU path.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -16,6 +17,7 @@
 #include "../../include/trx_b200.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_lower.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_fuse.h"
+#include "../../robio_2021_dexopt_b200/csrc/trx_direct.h"
 #include "../../robio_2021_dexopt_b200/csrc/vm_exec.cuh"
 
 namespace {
@@ -97,6 +99,36 @@ int emu_fused_create(const void *prog, size_t prog_n, const void *prep, size_t p
     return fail(TRX_ERR_INVALID, e.what());
   }
 }
+// objective lowering step of the product (trx_direct.h) on serialised tapes: the adjoint reads forward
+// operands in place.  Returns malloc'ed blobs of the rewritten prep and bprop programs; stats3 =
+// {prepare instructions dropped, arguments redirected, reverse_mul rewritten}.
+int emu_direct_prepare(const void *prep, size_t prep_n, const void *bprop, size_t bprop_n, void **out_prep,
+                       size_t *out_prep_n, void **out_bprop, size_t *out_bprop_n, uint64_t *stats3) {
+  try {
+    trxfile::Program p_prep, p_bprop;
+    trxfile::decodeProgram(prep, prep_n, p_prep);
+    trxfile::decodeProgram(bprop, bprop_n, p_bprop);
+    trx::DirectStats st;
+    trx::directPrepare(p_prep, p_bprop, st);
+    std::vector<uint8_t> a, b;
+    trxfile::encodeProgram(p_prep, a);
+    trxfile::encodeProgram(p_bprop, b);
+    *out_prep = std::malloc(a.size());
+    *out_bprop = std::malloc(b.size());
+    std::memcpy(*out_prep, a.data(), a.size());
+    std::memcpy(*out_bprop, b.data(), b.size());
+    *out_prep_n = a.size();
+    *out_bprop_n = b.size();
+    stats3[0] = st.n_prepare_dropped;
+    stats3[1] = st.n_arguments_redirected;
+    stats3[2] = st.n_mul_rewritten;
+  } catch (const std::exception &e) {
+    return fail(TRX_ERR_INVALID, e.what());
+  }
+  return TRX_OK;
+}
+void emu_free(void *p) { std::free(p); }
+
 void emu_program_destroy(emu_program *p) { delete p; }
 int emu_program_buffer_bytes(const emu_program *p, int which, uint64_t lanes, uint64_t *bytes) {
   *bytes = p->layout(which).wideElems(lanes) * 8;

@@ -109,6 +109,25 @@ class EmuEngine:
                                               c.c_int, c.c_int, c.c_int, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p)]
         self.warps = warps
 
+    def direct_prepare(self, bundle):
+        """(prep blob, bprop blob, stats) after the product's objective lowering step trx_direct.h"""
+        c = ctypes
+        f = self.lib.emu_direct_prepare
+        f.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.POINTER(c.c_void_p), c.POINTER(c.c_size_t),
+                      c.POINTER(c.c_void_p), c.POINTER(c.c_size_t), c.POINTER(c.c_uint64)]
+        self.lib.emu_free.argtypes = [c.c_void_p]
+        prep, bprop = bundle.programs["prep"], bundle.programs["bprop"]
+        b0, b1 = c.create_string_buffer(prep, len(prep)), c.create_string_buffer(bprop, len(bprop))
+        o0, o1, n0, n1 = c.c_void_p(), c.c_void_p(), c.c_size_t(), c.c_size_t()
+        stats = (c.c_uint64 * 3)()
+        if f(b0, len(prep), b1, len(bprop), c.byref(o0), c.byref(n0), c.byref(o1), c.byref(n1), stats) != 0:
+            raise RuntimeError(self.lib.emu_last_error().decode())
+        out = (c.string_at(o0, n0.value), c.string_at(o1, n1.value),
+               dict(prepare_dropped=stats[0], arguments_redirected=stats[1], mul_rewritten=stats[2]))
+        self.lib.emu_free(o0)
+        self.lib.emu_free(o1)
+        return out
+
     def compile_fused(self, bundle, ring_slots=192, sync_penalty=900):
         """(forward+prepare, adjoint) executables from the objective's fused lowering"""
         blobs = [bundle.programs[n] for n in ("prog", "prep", "bprop")]

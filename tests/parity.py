@@ -61,7 +61,7 @@ def tile_arrays(bundle, key):
     return out
 
 
-def check_problem(engine, bundle, n_tiles=None, check_tangent=True, compile_bprop=None):
+def check_problem(engine, bundle, n_tiles=None, check_tangent=True, compile_bprop=None, blobs=None):
     """objective + gradient over several lane tiles: x_prog, x_prep, x_bprop as in solvers/gd.h:50-63.
     compile_bprop: alternative way to lower the adjoint tape (e.g. with accumulate folding)"""
     prog = bundle.view("prog")
@@ -71,9 +71,10 @@ def check_problem(engine, bundle, n_tiles=None, check_tangent=True, compile_bpro
         n_tiles = len(params)
     params, r_ref = params[:n_tiles], r_ref[:n_tiles]
     lanes = 8 * n_tiles
-    x_prog = engine.compile(bundle.programs["prog"])
-    x_prep = engine.compile(bundle.programs["prep"])
-    x_bprop = (compile_bprop or engine.compile)(bundle.programs["bprop"])
+    blobs = dict(bundle.programs, **(blobs or {}))  # blobs: rewritten tapes replacing the bundle's
+    x_prog = engine.compile(blobs["prog"])
+    x_prep = engine.compile(blobs["prep"])
+    x_bprop = (compile_bprop or engine.compile)(blobs["bprop"])
     mem = engine.createMemory(lanes)
     if prog.parameters:
         x_prog.parameterize(trxfile.tiles_to_wide(prog.parameters, params), mem)

@@ -72,6 +72,35 @@ def test_stream_layout_invariants(emu_engine, golden, fixture):
         emu_engine.compile(blob).check_streams()
 
 
+@pytest.mark.parametrize("fixture", ["optests_8d.trxb", "optests_d.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
+def test_adjoint_reads_forward_operands_in_place(emu_engine, golden, fixture):
+    """objective lowering step trx_direct.h: bprop arguments that name x_prep's operand copies are redirected
+    to the forward slots, reverse_mul becomes reverse_x_muld, the now useless prepare instructions go away;
+    the gradient stays the reference's"""
+    bundle = golden(fixture)
+    if fixture.startswith("optests"):
+        n = 0
+        for name, has_grad in ((l[0], l[1] == "grad") for l in parity.op_names(bundle)):
+            if not has_grad:
+                continue
+            pre = "op/%s/" % name
+            sub = type("B", (), {"programs": {"prep": bundle.programs[pre + "prep"], "bprop": bundle.programs[pre + "bprop"]}})
+            prep, bprop, stats = emu_engine.direct_prepare(sub)
+            n += stats["prepare_dropped"]
+            x_prog = emu_engine.compile(bundle.programs[pre + "prog"])
+            mem = emu_engine.createMemory(8)
+            x_prog.run(bundle.arrays[pre + "x"], mem)
+            emu_engine.compile(prep).execute(mem)
+            gx = emu_engine.compile(bprop).run(bundle.arrays[pre + "gy"], mem)
+            parity.assert_close(gx, bundle.arrays[pre + "gx"], name + " reverse, operands in place")
+        assert n >= 10  # mul, the vec3 / quat / twist products, gate, ...
+        return
+    prep, bprop, stats = emu_engine.direct_prepare(bundle)
+    assert stats["prepare_dropped"] > 0 and stats["arguments_redirected"] + stats["mul_rewritten"] > 0
+    assert emu_engine.compile(prep).stat("n_instructions") < emu_engine.compile(bundle.programs["prep"]).stat("n_instructions")
+    parity.check_problem(emu_engine, bundle, check_tangent=False, blobs={"prep": prep, "bprop": bprop})
+
+
 def test_level_schedule_is_shallower_than_the_tape(emu_engine, golden):
     bundle = golden("dexsyn_small.trxb.xz")
     x = emu_engine.compile(bundle.programs["prog"])
