@@ -19,6 +19,7 @@
 // constant copy of SimpleEngine::_execute, simple.cpp:27-30).
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -127,6 +128,7 @@ struct LoweredProgram {
   uint32_t ring_doubles = 0;  // per-warp on-chip slot ring (doubles); 0 = every slot in the memory image
   uint64_t n_prefetch_lines = 0;
   uint32_t page_words = 0;  // stream page size the records were laid out for (0 = unpaged)
+  uint64_t n_copies_forwarded = 0;  // reads redirected from a copy to its source (fold_accumulate)
   uint64_t n_folded = 0;   // move/add instructions folded into their producer's output (fold_accumulate)
   uint64_t n_dropped = 0;  // instructions without outputs, not lowered
   uint64_t n_chained = 0;  // instructions appended to a chain (each saved a level boundary)
@@ -221,20 +223,124 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   }
   out.n_instructions = n_decoded;
 
-  // ---- 2b. accumulate folding (see LowerOptions)
-  std::vector<uint64_t> code(src.code);        // argument addresses after folding
+  // ---- 2b. copy propagation and accumulate folding (see LowerOptions)
+  std::vector<uint64_t> code(src.code);        // argument addresses after the rewrites
+  std::vector<uint64_t> base;                  // ... after copy propagation: what the folding patterns match on
   if (opt.fold_accumulate && opt.ring_slots == 0 && opt.pool_slots == 0) {
+    // -- copy propagation.  An output that is a plain copy of an input (move; the gradient copies of
+    // reverse_move and reverse_add) is forwarded to its readers: they read the source instead, as long as
+    // neither slot was written in between, and a copy instruction whose every output lost all its readers is
+    // dropped.  This also turns the reference's  `move g -> t2 ; add t2, tmp -> g`  into the in-place add.
+    {
+      struct CopyOf {
+        uint64_t source;
+        uint32_t source_version, own_version, inst, k_out, bytes;
+      };
+      struct CopyRule {
+        int k_out, k_in;
+      };
+      auto copyRules = [&](uint16_t o, CopyRule *r) -> int {
+        switch (o) {
+          case OP_MOVE: case OP_MOVE_MAT3: case OP_MOVE_VEC3: case OP_MOVE_QUAT: case OP_MOVE_POSE: case OP_MOVE_TWIST:
+            r[0] = {1, 0};
+            return 1;
+          case OP_R_MOVE: case OP_R_MOVE_MAT3: case OP_R_MOVE_VEC3: case OP_R_MOVE_QUAT: case OP_R_MOVE_POSE: case OP_R_MOVE_TWIST:
+            r[0] = {0, 1};
+            return 1;
+          case OP_R_ADD: case OP_R_ADD_VEC3: case OP_R_ADD_TWIST:
+            r[0] = {0, 2};
+            r[1] = {1, 2};
+            return 2;
+          default:
+            return 0;
+        }
+      };
+      std::unordered_map<uint64_t, uint32_t> version, n_writes, n_reads;
+      version.reserve(src.code.size());
+      std::unordered_set<uint64_t> port_slots;
+      for (auto *ports : {&src.inputs, &src.parameters, &src.outputs, &src.constants})
+        for (auto &p : *ports)
+          for (uint64_t a = p.address; a < p.address + p.size; a += 8) port_slots.insert(a);
+      auto forEachSlot = [&](const Inst &in, size_t k, const std::function<void(uint64_t)> &f) {
+        const ArgSig &a = table[ops[in.op].opcode].args[k];
+        const uint64_t addr = src.code[in.code_at + k];
+        if (!isBlock(a.kind)) {
+          f(addr);
+          return;
+        }
+        const uint32_t eb = blockElemBytes(a.kind, 8), size = src.ops[in.op].args[k].size;
+        for (uint32_t off = 0; off < size; off += eb) f(addr + off);
+      };
+      for (auto &in : insts) {
+        const OpSig &sig = table[ops[in.op].opcode];
+        for (size_t k = 0; k < sig.args.size(); k++)
+          forEachSlot(in, k, [&](uint64_t a) { (sig.args[k].is_input ? n_reads : n_writes)[a]++; });
+      }
+      std::unordered_map<uint64_t, CopyOf> copy_of;
+      std::vector<std::array<uint32_t, 2>> redirected(insts.size(), std::array<uint32_t, 2>{0, 0});
+      std::vector<uint8_t> is_copy(insts.size(), 0);
+      for (uint32_t i = 0; i < insts.size(); i++) {
+        const Inst &in = insts[i];
+        const OpRef &o = ops[in.op];
+        const OpSig &sig = table[o.opcode];
+        // readers first: an instruction reads its inputs before it writes
+        if (!sig.coop)
+          for (size_t k = 0; k < sig.args.size(); k++) {
+            if (!sig.args[k].is_input || sig.args[k].kind != ARG_T) continue;
+            auto c = copy_of.find(code[in.code_at + k]);
+            if (c == copy_of.end()) continue;
+            const CopyOf &co = c->second;
+            if (version[co.source] != co.source_version || version[c->first] != co.own_version) continue;
+            if (co.bytes != src.ops[in.op].args[k].size) continue;
+            code[in.code_at + k] = co.source;
+            redirected[co.inst][co.k_out]++;
+            out.n_copies_forwarded++;
+          }
+        for (size_t k = 0; k < sig.args.size(); k++)
+          if (!sig.args[k].is_input) forEachSlot(in, k, [&](uint64_t a) { version[a]++; });
+        CopyRule rules[2];
+        const int nr = copyRules(o.opcode, rules);
+        for (int q = 0; q < nr; q++) {
+          const uint64_t t = src.code[in.code_at + rules[q].k_out], s_ = code[in.code_at + rules[q].k_in];
+          if (t == s_) continue;
+          is_copy[i] = 1;
+          copy_of[t] = {s_, version[s_], version[t], i, (uint32_t)q, src.ops[in.op].args[rules[q].k_out].size};
+        }
+      }
+      // drop the copy instructions nobody reads any more
+      size_t w = 0;
+      for (uint32_t i = 0; i < insts.size(); i++) {
+        bool drop = false;
+        if (is_copy[i]) {
+          const Inst &in = insts[i];
+          CopyRule rules[2];
+          const int nr = copyRules(ops[in.op].opcode, rules);
+          drop = true;
+          for (int q = 0; q < nr && drop; q++) {
+            const uint64_t t = src.code[in.code_at + rules[q].k_out];
+            drop = n_writes[t] == 1 && !port_slots.count(t) && redirected[i][q] == n_reads[t] &&
+                   t != code[in.code_at + rules[q].k_in];
+          }
+          // both outputs of reverse_add into the same slot would make the counts ambiguous: keep it
+          if (nr == 2 && src.code[in.code_at + rules[0].k_out] == src.code[in.code_at + rules[1].k_out]) drop = false;
+        }
+        if (drop) out.n_folded++;
+        else insts[w++] = insts[i];
+      }
+      insts.resize(w);
+    }
+    base = code;
     struct SlotUse {
       uint32_t writer = 0, reader = 0;
       uint32_t nw = 0, nr = 0;
     };
     std::unordered_map<uint64_t, SlotUse> use;
-    use.reserve(src.code.size());
+    use.reserve(base.size());
     for (uint32_t i = 0; i < insts.size(); i++) {
       const Inst &in = insts[i];
       const OpSig &sig = table[ops[in.op].opcode];
       for (size_t k = 0; k < sig.args.size(); k++) {
-        uint64_t addr = src.code[in.code_at + k];
+        uint64_t addr = base[in.code_at + k];
         if (isBlock(sig.args[k].kind)) {
           uint32_t eb = blockElemBytes(sig.args[k].kind, 8), size = src.ops[in.op].args[k].size;
           for (uint32_t off = 0; off < size; off += eb) {
@@ -299,23 +405,23 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
           const OpSig &jsig = table[ops[J.op].opcode];
           if (jsig.coop) return false;
           for (size_t k = 0; k < jsig.args.size(); k++)
-            if (code[J.code_at + k] == dst || src.code[J.code_at + k] == dst) return false;
+            if (code[J.code_at + k] == dst || base[J.code_at + k] == dst) return false;
         }
         return true;
       };
       if (isAdd(bo.opcode)) {
         // move dst -> t2 ; add t2, tmp -> dst   becomes the in-place   add dst, tmp -> dst
         // (every operator loads all its inputs before it stores; vm_ops.def)
-        const uint64_t dst = src.code[B.code_at + 2];
+        const uint64_t dst = base[B.code_at + 2];
         for (int q = 0; q < 2; q++) {
-          const uint64_t t2 = src.code[B.code_at + q], other = src.code[B.code_at + 1 - q];
+          const uint64_t t2 = base[B.code_at + q], other = base[B.code_at + 1 - q];
           if (t2 == dst || other == dst || other == t2) continue;
           const uint32_t mi = soleWriter(t2, bi);
           if (mi == ~0u || mi >= bi || bi - mi > 16 || dropped[mi] || inPort(t2, bytes)) continue;
           const Inst &M = insts[mi];
           const OpRef &mo = ops[M.op];
           if (!isMove(mo.opcode) || mo.lane_width != bo.lane_width || table[mo.opcode].args[0].comps != comps) continue;
-          if (src.code[M.code_at] != dst || src.code[M.code_at + 1] != t2) continue;
+          if (base[M.code_at] != dst || base[M.code_at + 1] != t2) continue;
           if (!untouched(mi, ~0u, dst)) continue;
           code[B.code_at + q] = dst;
           dropped[mi] = 1;
@@ -325,7 +431,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
         continue;
       }
       // A -> tmp ; move tmp -> dst   becomes   A -> dst
-      const uint64_t tmp = src.code[B.code_at], dst = src.code[B.code_at + 1];
+      const uint64_t tmp = base[B.code_at], dst = base[B.code_at + 1];
       if (tmp == dst) continue;
       const uint32_t ai = soleWriter(tmp, bi);
       if (ai == ~0u || ai >= bi || bi - ai > 16 || dropped[ai]) continue;
@@ -341,7 +447,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
       for (size_t k = 0; k < asig.args.size(); k++) {
         if (code[A.code_at + k] == dst) dst_used = true;  // A reads dst or already writes it
         if (asig.args[k].is_input) continue;
-        if (src.code[A.code_at + k] == tmp && asig.args[k].comps == comps && asig.args[k].kind == ARG_T) k_out = (int)k;
+        if (base[A.code_at + k] == tmp && asig.args[k].comps == comps && asig.args[k].kind == ARG_T) k_out = (int)k;
       }
       if (k_out < 0 || dst_used || inPort(tmp, bytes) || !untouched(ai, ~0u, dst)) continue;
       code[A.code_at + k_out] = dst;
