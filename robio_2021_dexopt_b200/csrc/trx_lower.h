@@ -99,7 +99,7 @@ struct LowerOptions {
   // appended to that chain instead of opening a new level: the chain's records run back to back on the
   // same threads (thread = (sub-instruction, lane)), so program order replaces the block barrier.
   // Maximum chain length; <= 1 turns chaining off.
-  uint32_t chain_cap = 2;  // measured on B200 (profiles/README.md): 2..4 are within 3%, longer chains lose to load imbalance
+  uint32_t chain_cap = 4;  // measured on B200 (profiles/README.md): best for the folded adjoint; 5 and more lose to load imbalance
   // stream pages (words, power of two; 0 = unpaged): no record straddles a page boundary and every
   // warp's stream starts on one, so the kernel can stage whole pages in shared memory ahead of the
   // interpreter and read record headers and argument words from there
