@@ -14,7 +14,9 @@
 // Values are untouched: every reverse rule sees bit-identical operands.  What disappears is the copy traffic
 // (a DRAM read and a DRAM write per saved operand) and about three quarters of the prep launch.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <initializer_list>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -199,6 +201,46 @@ inline void directPrepare(trxfile::Program &prep, trxfile::Program &bprop, Direc
   }
   prep.code.swap(pcode);
   prep.n_instructions = kept;
+}
+
+// True when no instruction output and no input / parameter port of the given programs overlaps a
+// constant slot of any of them: an objective that runs exactly these programs on one Memory may then upload
+// the constants once instead of with every execute (the reference copies them every time, simple.cpp:27-30).
+inline bool constantsAreNeverWritten(std::initializer_list<const trxfile::Program *> programs) {
+  std::vector<std::pair<uint64_t, uint64_t>> ranges;
+  for (auto *p : programs)
+    for (auto &c : p->constants) ranges.push_back({c.address, c.address + c.size});
+  if (ranges.empty()) return true;
+  std::sort(ranges.begin(), ranges.end());
+  size_t w = 0;
+  for (size_t i = 0; i < ranges.size(); i++) {
+    if (w && ranges[i].first <= ranges[w - 1].second) ranges[w - 1].second = std::max(ranges[w - 1].second, ranges[i].second);
+    else ranges[w++] = ranges[i];
+  }
+  ranges.resize(w);
+  auto overlaps = [&](uint64_t a, uint64_t size) {
+    if (!size) return false;
+    auto it = std::lower_bound(ranges.begin(), ranges.end(), std::make_pair(a + size, (uint64_t)0));
+    if (it == ranges.begin()) return false;
+    --it;
+    return it->second > a;
+  };
+  for (auto *p : programs) {
+    // inputs and parameters are written by the port scatter (and bprop's inputs by the adjoint seeds);
+    // outputs are only read
+    for (auto *ports : {&p->inputs, &p->parameters})
+      for (auto &q : *ports)
+        if (overlaps(q.address, q.size)) return false;
+    for (uint64_t pc = 0; pc < p->code.size();) {
+      const uint64_t oi = p->code[pc];
+      if (oi >= p->ops.size()) return false;
+      const auto &op = p->ops[oi];
+      for (size_t k = 0; k < op.args.size(); k++)
+        if (!op.args[k].is_input && overlaps(p->code[pc + 1 + k], op.args[k].size)) return false;
+      pc += 1 + op.args.size();
+    }
+  }
+  return true;
 }
 
 }  // namespace trx

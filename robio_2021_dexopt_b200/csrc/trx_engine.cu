@@ -1093,13 +1093,18 @@ trx_status trx_parameterize_device(const trx_program *p, trx_memory *m, const vo
   return scatterDevice(p, m, TRX_BUF_PARAMETER, (const double *)d, bytes, (cudaStream_t)stream);
 }
 
-trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) {
+static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_, bool upload_constants);
+trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) { return executeImpl(p, m, stream_, true); }
+
+// upload_constants = false: the caller knows that this memory already holds the program's constants and
+// that nothing has overwritten them (objectives, after their first evaluation)
+static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_, bool upload_constants) {
   if (!p || !m) return fail(TRX_ERR_INVALID, "bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   TRX_CUDA(cudaSetDevice(m->device));
   trx_status s = ensureTileStride(m, p->low.memory_size, stream);
   if (s != TRX_OK) return s;
-  uint32_t nc = (uint32_t)p->low.const_idx.size();
+  uint32_t nc = upload_constants ? (uint32_t)p->low.const_idx.size() : 0;
   if (nc) {
     dim3 grid((nc + 255) / 256, (unsigned)m->n_tiles);
     trx_const_kernel<<<grid, 256, 0, stream>>>(p->d_const_idx, p->d_const_bits, nc, m->d_mem, m->tile_stride);
@@ -1217,6 +1222,8 @@ struct trx_objective {
   trx_memory *mem = nullptr;
   double *d_x = nullptr, *d_params = nullptr, *d_out = nullptr, *d_partial = nullptr;
   trx::DirectStats direct;
+  bool consts_static = false;    // no tape instruction or port of the objective overlaps a constant slot
+  bool consts_resident = false;  // ... and the memory holds them since the first evaluation
   double *h_x = nullptr, *h_out = nullptr;  // pinned
   uint64_t param_elems = 0;
   SeedElem *d_seed = nullptr;
@@ -1268,6 +1275,8 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       // the adjoint reads forward operands in place instead of through x_prep's copies (trx_direct.h)
       static int direct_env = getenv("TRX_DIRECT") ? atoi(getenv("TRX_DIRECT")) : 1;
       if (direct_env && !o->fused) trx::directPrepare(p_prep, p_bprop, o->direct);
+      static int static_env = getenv("TRX_STATIC_CONSTS") ? atoi(getenv("TRX_STATIC_CONSTS")) : 1;
+      o->consts_static = static_env && trx::constantsAreNeverWritten({&p_prog, &p_prep, &p_bprop});
     } catch (const std::exception &e) {
       return fail(TRX_ERR_INVALID, e.what());
     }
@@ -1379,6 +1388,7 @@ trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t 
   else if (k == "parameter_bytes") *value = o->param_elems * 8;
   else if (k == "device_bytes") *value = o->mem->tile_stride * o->mem->n_tiles * 8;
   else if (k == "fused") *value = o->fused ? 1 : 0;
+  else if (k == "consts_static") *value = o->consts_static ? 1 : 0;
   else if (k == "direct.n_prepare_dropped") *value = o->direct.n_prepare_dropped;
   else if (k == "direct.n_arguments_redirected") *value = o->direct.n_arguments_redirected;
   else if (k == "direct.n_mul_rewritten") *value = o->direct.n_mul_rewritten;
@@ -1437,16 +1447,20 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
     if (s != TRX_OK) return s;
     cudaEvent_t *pe = o->profiling ? &o->prof_events[c * 4] : nullptr;
     if (pe) cudaEventRecord(pe[0], stream);
-    if ((s = trx_execute(o->prog, m, stream_)) != TRX_OK) return s;
+    // constants: uploaded by every execute as the reference does (simple.cpp:27-30), except when this
+    // objective has proven that nothing it runs can overwrite one -- then once is enough
+    const bool consts = !o->consts_resident;
+    if ((s = executeImpl(o->prog, m, stream_, consts)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[1], stream);
     trx_seed_kernel<<<dim3((unsigned)chunk_tiles, kSeedSplit), 256, 0, stream>>>(
         o->d_seed, o->n_seed, m->d_mem, m->tile_stride, (c == 0 && o->scalar_rows) ? 1 : 0,
         o->d_partial + c * chunk_tiles * kSeedSplit);
     g_launches++;
-    if (o->prep && (s = trx_execute(o->prep, m, stream_)) != TRX_OK) return s;
+    if (o->prep && (s = executeImpl(o->prep, m, stream_, consts)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[2], stream);
-    if ((s = trx_execute(o->bprop, m, stream_)) != TRX_OK) return s;
+    if ((s = executeImpl(o->bprop, m, stream_, consts)) != TRX_OK) return s;
     if (pe) cudaEventRecord(pe[3], stream);
+    if (c + 1 == o->n_chunks && o->consts_static) o->consts_resident = true;
     uint32_t n = o->bprop->n_elems[TRX_BUF_OUTPUT];
     dim3 grid((n + 255) / 256, 1);
     trx_gather_kernel<<<grid, 256, 0, stream>>>(o->bprop->d_elems[TRX_BUF_OUTPUT], n, d_out + 1, o->lanes, 0, m->d_mem,
