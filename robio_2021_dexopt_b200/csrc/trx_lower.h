@@ -86,9 +86,11 @@ inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32
 
 struct LowerOptions {
   uint32_t n_warps = 16;
-  // software prefetch: operands of level L+D that already exist are pulled into L2 while level L runs
-  // (the schedule is static, so the addresses are known); 0 = off
-  uint32_t prefetch_distance = 0;  // measured: no gain on B200 for these tapes (profiles/README.md)
+  // software prefetch: operands of level L+D that already exist when level L starts (values of an earlier
+  // program, constants, ports) are pulled into L2 while level L runs -- the schedule is static, so the
+  // addresses are known.  0 = off.  Measured on the final kernel (profiles/README.md): -7 % per evaluation
+  // at D = 1..4 (the adjoint reads the forward tape from DRAM); programs with a single level skip it.
+  uint32_t prefetch_distance = 2;
   // CTA-wide on-chip slot cache (shared memory): a FIFO ring of the most recently produced lane-typed
   // values plus a pool of the tape's distinct constants.  Every result is still written to the memory
   // image (the reference's persist-everything contract); reads are served on chip when the lowering can
@@ -601,7 +603,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   };
   // 128-byte lines (index = byte address / 128) that level L reads and that exist `prefetch_distance`
   // levels earlier
-  const uint32_t PD = opt.prefetch_distance;
+  const uint32_t PD = n_levels > 1 ? opt.prefetch_distance : 0;
   std::vector<std::vector<uint32_t>> level_lines(PD ? n_levels + 2 : 0);
   if (PD)
     for (auto &in : insts) {
