@@ -40,8 +40,8 @@ UNIT = "timestep*rollouts/s"
 # compulsory HBM traffic per timestep*rollout with one state checkpoint written by
 # the forward sweep and read back by the adjoint: 2 * 8 * (n_q + 13 * n_dyn) bytes, n_q = 29, n_dyn = 1
 B_ALG = 2 * 8 * (29 + 13)
-# measured DRAM traffic of the adjoint launch per unit (profiles/README.md): 3.210 GB / (32 frames * 1024 rollouts)
-NCU_BPROP_DRAM_BYTES_PER_UNIT = (1.860485e9 + 1.349167e9) / (32 * 1024)
+# measured DRAM traffic of the adjoint launch per unit (profiles/README.md): 3.820 GB / (32 frames * 1024 rollouts)
+NCU_BPROP_DRAM_BYTES_PER_UNIT = (2.465697e9 + 1.354105e9) / (32 * 1024)
 
 
 def measured_peak_hbm():
@@ -285,7 +285,7 @@ def main():
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of the adjoint launch from the committed ncu --set full
-            # capture (profiles/ncu_full_r1_staged_T32_raw.csv: 3.210 GB for 32 frames x 1024 rollouts), scaled
+            # capture (profiles/ncu_full_r1_staged_T32_raw.csv: 3.820 GB for 32 frames x 1024 rollouts), scaled
             # to this launch's units; only for the default dense-fused generic lowering it was captured on
             "traffic": (NCU_BPROP_DRAM_BYTES_PER_UNIT * units_per_launch if (not FUSED and FUSE_DENSE) else None),
             "traffic_source": "profiles/ncu_full_r1_staged_T32_raw.csv, per unit x units_per_launch",
