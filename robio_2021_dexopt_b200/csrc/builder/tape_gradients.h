@@ -301,7 +301,20 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, b
     auto index = opIndex(hprop);
     for (auto *part : {&fprop, &bprop}) {
       for (auto &in : decode(*part)) {
-        hprop.code.push_back(internOp(hprop, index, part->ops[in.op].name));
+        const auto &pop = part->ops[in.op];
+        uint16_t popcode;
+        uint32_t plw;
+        trx::findOp(pop.name, popcode, plw);
+        uint32_t id;
+        if (trx::opTable()[popcode].coop) {
+          // block operators carry their block sizes in the operator table entry
+          std::vector<uint32_t> sizes;
+          for (auto &a : pop.args) sizes.push_back(a.size);
+          id = internBlockOp(hprop, index, pop.name, sizes);
+        } else {
+          id = internOp(hprop, index, pop.name);
+        }
+        hprop.code.push_back(id);
         for (uint32_t k = 0; k < in.n_args; k++) hprop.code.push_back(part->code[in.code_at + k]);
         hprop.n_instructions++;
       }

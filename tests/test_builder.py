@@ -62,3 +62,27 @@ def test_built_programs_reproduce_reference_numbers(emu_engine, golden, fixture,
         assert int(mine.meta()["n_prog_instructions"]) < 0.7 * n_ref
         assert any(o.name == "forward_x_dense_8d" for o in mine.view("fprop").ops)
         assert any(o.name == "forward_x_dense_8d" for o in mine.view("hprop").ops)
+
+
+@pytest.mark.parametrize("fuse_dense", [0, 1])
+def test_hprop_is_bprop_after_fprop(emu_engine, golden, fuse_dense):
+    """x_hprop = x_fprop ; x_bprop on one memory (gradients.cpp:344-362): J^T J v from the single program equals
+    the two sweeps run one after the other, for the reference expansion and for dense-fused tapes
+    (forward_x_dense / reverse_x_dense)"""
+    import numpy as np
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("dexsyn_small.trxb.xz")
+    mine = pkg.build_dexsyn(frames=3, hidden=4, extra_fixed=4, fuse_dense=fuse_dense)
+    x = {n: emu_engine.compile(mine.programs[n]) for n in ("prog", "prep", "fprop", "bprop", "hprop")}
+    # one lane tile: over several tiles a single hprop program would count the lane-independent residual
+    # rows once per tile (the objective call counts them once; DESIGN.md row N4)
+    mem = emu_engine.createMemory(8)
+    x["prog"].parameterize(trxfile.tiles_to_wide(mine.view("prog").parameters, parity.tile_arrays(ref, "params")[:1]), mem)
+    x["prog"].run(ref.arrays["x"], mem)
+    x["prep"].execute(mem)
+    v = np.random.default_rng(5).standard_normal(ref.arrays["x"].size)
+    two_sweeps = x["bprop"].run(x["fprop"].run(v, mem), mem)
+    one_program = x["hprop"].run(v, mem)
+    assert np.any(one_program != 0.0)
+    parity.assert_close(one_program, two_sweeps, "J^T J v", rtol=1e-12)
