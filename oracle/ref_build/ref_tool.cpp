@@ -266,7 +266,7 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
 // Runs K lane tiles through the reference engine and stores the golden arrays.
 static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std::vector<double> &x, size_t n_param_lane,
                        int tiles, uint64_t seed, const std::string &param_kind, int gd_steps = 0,
-                       double learning_rate = 0.01) {
+                       double learning_rate = 0.01, bool gd_keep_all = true) {
   dexsyn::Rng rng(seed);
   RefRunner run(gs);
   size_t nx = portElements(gs.prog.inputs());
@@ -364,7 +364,7 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
       run.x_accu->run(ab, run.memory, xn);
       xk = xn;
       losses.push_back(loss);
-      iterates.insert(iterates.end(), xk.begin(), xk.end());
+      if (gd_keep_all || step + 1 == gd_steps) iterates.insert(iterates.end(), xk.begin(), xk.end());
     }
     bundle.arrays.emplace_back("gd/loss", losses);
     bundle.arrays.emplace_back("gd/x", iterates);
@@ -400,10 +400,12 @@ static int cmdRecord(const std::string &path, const std::map<std::string, std::s
     meta += "n_prog_instructions=" + std::to_string(n) + "\n";
   }
   bundle.texts.emplace_back("meta", meta);
-  gs.addTo(bundle);
+  // programs=0: values only (the product records the same problem itself, trx_dexsyn_build);
+  // gd_keep=last: store only the last gradient-descent iterate (all losses are kept)
+  if (getI(kv, "programs", 1)) gs.addTo(bundle);
   if (tiles > 0)
     goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem,
-               (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01));
+               (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01), getS(kv, "gd_keep", "all") == "all");
   else bundle.arrays.emplace_back("x", x);
   trxfile::writeBundle(bundle, path);
   std::cerr << meta;
