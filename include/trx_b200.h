@@ -194,6 +194,20 @@ enum {
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
                                 int device, int flags, trx_objective **out);
+/* The same objective in re-rolled form (csrc/rollout/rollout_plan.h): where
+ * DexLearn::_runBatch (dexopt/src/dexlearn.h:393-422) unrolls its frame loop onto one flat tape, the product's
+ * assembly can also emit ONE frame program plus the state carried between frames; it is evaluated by the
+ * hand-written forward / adjoint frame kernels of csrc/trx_rollout.cu (forward kinematics, contacts and the
+ * adjoint fused, policy layers on the FP64 tensor cores, one state checkpoint per frame in HBM).  `options` is
+ * the problem description trx_dexsyn_build takes; results equal those of trx_objective_create over the tapes of
+ * trx_dexsyn_build(options).  TRX_ERR_UNSUPPORTED when the problem has no re-rolled form (dropout masks,
+ * outer > 1, no policy): use the tape objective.  Every other trx_objective_* call works on it. */
+trx_status trx_objective_create_rollout(const char *options, uint64_t lanes, uint64_t max_device_bytes, int device,
+                                        int flags, trx_objective **out);
+/* r = x_prog->run(x) (tractor/include/tractor/solvers/gd.h:50-53): the residual vector of all rollouts in the
+ * wide layout (lane-independent rows once, then [row][rollout]); info key "residual_elems" gives its length.
+ * Re-rolled objectives only (tape objectives: trx_execute + trx_output on the prog executable). */
+trx_status trx_objective_residuals(trx_objective *o, const double *x, double *r, uint64_t r_bytes, void *stream);
 void trx_objective_destroy(trx_objective *o);
 /* keys: n_x lanes chunk_lanes n_chunks parameter_bytes device_bytes launches_per_evaluation fused,
  * and prog.<stat> / prep.<stat> / bprop.<stat> with the keys of trx_program_stat */

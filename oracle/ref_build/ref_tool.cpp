@@ -266,7 +266,7 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
 // Runs K lane tiles through the reference engine and stores the golden arrays.
 static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std::vector<double> &x, size_t n_param_lane,
                        int tiles, uint64_t seed, const std::string &param_kind, int gd_steps = 0,
-                       double learning_rate = 0.01, bool gd_keep_all = true) {
+                       double learning_rate = 0.01, bool gd_keep_all = true, bool keep_dr = true) {
   dexsyn::Rng rng(seed);
   RefRunner run(gs);
   size_t nx = portElements(gs.prog.inputs());
@@ -329,7 +329,7 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
     bundle.arrays.emplace_back(s + "params", params);
     bundle.arrays.emplace_back(s + "r", r);
     bundle.arrays.emplace_back(s + "g", g);
-    bundle.arrays.emplace_back(s + "dr", dr);
+    if (keep_dr) bundle.arrays.emplace_back(s + "dr", dr);
   }
   bundle.arrays.emplace_back("g_total", g_total);
   bundle.arrays.emplace_back("h_total", h_total);
@@ -401,11 +401,13 @@ static int cmdRecord(const std::string &path, const std::map<std::string, std::s
   }
   bundle.texts.emplace_back("meta", meta);
   // programs=0: values only (the product records the same problem itself, trx_dexsyn_build);
-  // gd_keep=last: store only the last gradient-descent iterate (all losses are kept)
+  // gd_keep=last: store only the last gradient-descent iterate (all losses are kept);
+  // keep_dr=0: drop the per-tile tangent residuals (h_total = J^T J dx stays)
   if (getI(kv, "programs", 1)) gs.addTo(bundle);
   if (tiles > 0)
     goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem,
-               (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01), getS(kv, "gd_keep", "all") == "all");
+               (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01), getS(kv, "gd_keep", "all") == "all",
+               getI(kv, "keep_dr", 1) != 0);
   else bundle.arrays.emplace_back("x", x);
   trxfile::writeBundle(bundle, path);
   std::cerr << meta;

@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+TRANSLATION_UNITS = ["trx_engine.cu", "trx_rollout.cu", "trx_builder.cpp"]
+OBJ_DIR = os.path.join(HERE, "_obj")
+
+
 def sources():
     deps = []
     for root, _, files in os.walk(CSRC):
@@ -42,16 +46,44 @@ def stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+def _unit_deps(unit: str):
+    """files a translation unit is rebuilt for: found by scanning its #include "..." closure"""
+    import re
+    seen, todo = set(), [os.path.join(CSRC, unit)]
+    while todo:
+        path = os.path.normpath(todo.pop())
+        if path in seen or not os.path.exists(path):
+            continue
+        seen.add(path)
+        with open(path, errors="replace") as f:
+            for inc in re.findall(r'#\s*include\s*"([^"]+)"', f.read()):
+                todo.append(os.path.join(os.path.dirname(path), inc))
+    return seen
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
+    """one object per translation unit (compiled in parallel, rebuilt only when its include closure
+    changed), then one link: csrc/*.cu|cpp -> _obj/*.o -> libtrx_b200.so"""
     if not force and not stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, "trx_engine.cu"), os.path.join(CSRC, "trx_builder.cpp"),
-                                 "-o", OUT + ".tmp"]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-c"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+        compile_flags = ["-Xptxas", "-v"] + compile_flags
+    jobs, objs = [], []
+    for unit in TRANSLATION_UNITS:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
+        objs.append(obj)
+        deps = _unit_deps(unit)
+        fresh = os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps)
+        if fresh and not force:
+            continue
+        jobs.append((unit, subprocess.Popen([nvcc] + compile_flags + [os.path.join(CSRC, unit), "-o", obj], cwd=CSRC)))
+    for unit, job in jobs:
+        if job.wait() != 0:
+            raise subprocess.CalledProcessError(job.returncode, "nvcc " + unit)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", OUT + ".tmp"])
     os.replace(OUT + ".tmp", OUT)
     return OUT
 

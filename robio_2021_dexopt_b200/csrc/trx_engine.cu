@@ -25,6 +25,7 @@
 #include "trx_fuse.h"
 #include "trx_direct.h"
 #include "vm_exec.cuh"
+#include "trx_rollout.h"
 
 namespace {
 
@@ -1211,6 +1212,8 @@ trx_status trx_memory_peek(trx_memory *m, uint64_t tile, uint64_t address, void 
 // ------------------------------------------------------------------ objective (solver-level glue)
 
 struct trx_objective {
+  // re-rolled rollout objective (trx_rollout.cu): when set, the tape members below are unused
+  trx_rollout *rollout = nullptr;
   // owned.  fused: prog = forward+prepare, prep = null, bprop = adjoint (trx_fuse.h);
   // otherwise the three programs lowered one by one as generic executables (trx_lower.h)
   trx_program *prog = nullptr, *prep = nullptr, *bprop = nullptr;
@@ -1361,6 +1364,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
 
 void trx_objective_destroy(trx_objective *o) {
   if (!o) return;
+  trxRolloutDestroy(o->rollout);
   trx_program_destroy(o->prog);
   trx_program_destroy(o->prep);
   trx_program_destroy(o->bprop);
@@ -1381,6 +1385,14 @@ void trx_objective_destroy(trx_objective *o) {
 trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t *value) {
   if (!o || !key || !value) return fail(TRX_ERR_INVALID, "bad argument");
   std::string k = key;
+  if (o->rollout && k != "n_x" && k != "lanes" && k != "parameter_bytes") {
+    if (k == "rerolled") { *value = 1; return TRX_OK; }
+    uint64_t v = trxRolloutInfo(o->rollout, key);
+    if (v == ~0ull) return fail(TRX_ERR_INVALID, "unknown key " + k);
+    *value = v;
+    return TRX_OK;
+  }
+  if (k == "rerolled") { *value = 0; return TRX_OK; }
   if (k == "n_x") *value = o->n_x;
   else if (k == "lanes") *value = o->lanes;
   else if (k == "chunk_lanes") *value = o->chunk_lanes;
@@ -1415,6 +1427,11 @@ trx_status trx_objective_info(const trx_objective *o, const char *key, uint64_t 
 // per-lane parameters of all `lanes` rollouts (wide layout), host pointer
 trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint64_t bytes, void *stream_) {
   if (!o || (!packed && bytes)) return fail(TRX_ERR_INVALID, "bad argument");
+  if (o->rollout) {
+    std::string err;
+    trx_status s = trxRolloutParameterize(o->rollout, packed, bytes, (cudaStream_t)stream_, err);
+    return s == TRX_OK ? s : fail(s, err);
+  }
   if (bytes != o->param_elems * 8)
     return fail(TRX_ERR_SIZE, "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
                                   std::to_string(o->param_elems * 8));
@@ -1434,6 +1451,13 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
   if (!o || !d_x || !d_out) return fail(TRX_ERR_INVALID, "bad argument");
   TRX_CUDA(cudaSetDevice(o->device));
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (o->rollout) {
+    std::string err;
+    uint64_t before = trxRolloutLaunches(o->rollout);
+    trx_status s = trxRolloutEvaluate(o->rollout, d_x, d_out, nullptr, nullptr, true, stream, err);
+    g_launches += trxRolloutLaunches(o->rollout) - before;
+    return s == TRX_OK ? s : fail(s, err);
+  }
   trx_memory *m = o->mem;
   const uint64_t chunk_tiles = m->n_tiles;
   for (uint64_t c = 0; c < o->n_chunks; c++) {
@@ -1502,6 +1526,7 @@ trx_status trx_objective_evaluate(trx_objective *o, const double *x, double *los
 // elapsed times of the last evaluation to running totals {prog, prep, bprop} in milliseconds.
 trx_status trx_objective_set_profiling(trx_objective *o, int enable) {
   if (!o) return fail(TRX_ERR_INVALID, "bad argument");
+  if (o->rollout) return fail(TRX_ERR_UNSUPPORTED, "the re-rolled objective is one launch: time it with events on the stream");
   TRX_CUDA(cudaSetDevice(o->device));
   o->profiling = enable != 0;
   if (o->profiling && o->prof_events.empty()) {
@@ -1547,6 +1572,60 @@ trx_status trx_objective_gd_steps(trx_objective *o, double *d_x, double *d_v, do
     g_launches++;
   }
   TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+// The re-rolled form of the objective (csrc/rollout, trx_rollout.cu): built from the problem description
+// instead of from flat tapes; every other trx_objective_* call works on it unchanged.
+trx_status trx_objective_create_rollout(const char *options, uint64_t lanes, uint64_t max_device_bytes, int device,
+                                        int flags, trx_objective **out) {
+  if (!options || !out) return fail(TRX_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  std::unique_ptr<trx_objective, void (*)(trx_objective *)> o(new trx_objective(), trx_objective_destroy);
+  o->scalar_rows = (flags & TRX_OBJECTIVE_NO_SCALAR_ROWS) == 0;
+  o->device = device;
+  o->lanes = lanes;
+  std::string err;
+  trx_status s = trxRolloutCreate(options, lanes, max_device_bytes, device, o->scalar_rows, &o->rollout, err);
+  if (s != TRX_OK) return fail(s, err);
+  o->n_x = trxRolloutInfo(o->rollout, "n_x");
+  o->param_elems = trxRolloutInfo(o->rollout, "parameter_elems");
+  o->chunk_lanes = trxRolloutInfo(o->rollout, "chunk_lanes");
+  o->n_chunks = trxRolloutInfo(o->rollout, "n_chunks");
+  TRX_CUDA(cudaMalloc(&o->d_x, std::max<uint64_t>(1, o->n_x) * 8));
+  TRX_CUDA(cudaMalloc(&o->d_out, (o->n_x + 1) * 8));
+  TRX_CUDA(cudaMallocHost(&o->h_x, std::max<uint64_t>(1, o->n_x) * 8));
+  TRX_CUDA(cudaMallocHost(&o->h_out, (o->n_x + 1) * 8));
+  for (auto &e : o->ev) TRX_CUDA(cudaEventCreate(&e));
+  *out = o.release();
+  return TRX_OK;
+}
+
+// r = x_prog->run(x) (solvers/gd.h:50-53) for all rollouts, to the host; wide layout
+trx_status trx_objective_residuals(trx_objective *o, const double *x, double *r, uint64_t r_bytes, void *stream_) {
+  if (!o || !x || !r) return fail(TRX_ERR_INVALID, "bad argument");
+  if (!o->rollout) return fail(TRX_ERR_UNSUPPORTED, "tape objectives: run the prog executable (trx_execute / trx_output)");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const uint64_t n = trxRolloutInfo(o->rollout, "residual_elems");
+  if (r_bytes != n * 8)
+    return fail(TRX_ERR_SIZE, "residual buffer size mismatch: got " + std::to_string(r_bytes) + " expected " + std::to_string(n * 8));
+  double *d_r = nullptr;
+  TRX_CUDA(cudaMalloc(&d_r, n * 8));
+  std::memcpy(o->h_x, x, o->n_x * 8);
+  cudaError_t e = cudaMemcpyAsync(o->d_x, o->h_x, o->n_x * 8, cudaMemcpyHostToDevice, stream);
+  std::string err;
+  trx_status s = TRX_OK;
+  if (e == cudaSuccess) {
+    uint64_t before = trxRolloutLaunches(o->rollout);
+    s = trxRolloutEvaluate(o->rollout, o->d_x, o->d_out, d_r, nullptr, false, stream, err);
+    g_launches += trxRolloutLaunches(o->rollout) - before;
+  }
+  if (e == cudaSuccess && s == TRX_OK) e = cudaMemcpyAsync(r, d_r, n * 8, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && s == TRX_OK) e = cudaStreamSynchronize(stream);
+  cudaFree(d_r);
+  if (s != TRX_OK) return fail(s, err);
+  if (e != cudaSuccess) return fail(TRX_ERR_CUDA, cudaGetErrorString(e));
   return TRX_OK;
 }
 

@@ -1,0 +1,687 @@
+// trx_rollout.cu -- the re-rolled rollout objective on sm_100a: one kernel evaluates residuals, loss and
+// J^T r of dexopt's policy-rollout objective for all rollouts, frame by frame, with every per-frame
+// intermediate on chip.
+//
+//   reference                                          here
+//   -------------------------------------------------  -------------------------------------------------
+//   x_prog / x_prep / x_bprop executables over a flat  one launch of trx_rollout_kernel: forward sweep over the
+//   write-once tape image (solvers/gd.h:50-63,         frames (state checkpoint per frame -> HBM), then the
+//   src/engines/simple.cpp:22-35)                      adjoint sweep, which recomputes each frame from its
+//                                                      checkpoint (csrc/rollout/rollout_frame.h)
+//   batch + dot4add + madd per weight                  policy layers as FP64 tensor-core tiles (DMMA m8n8k4) over
+//   (dexopt/src/tensor.h:134-172, ops.h:22-85)         the rollouts of the CTA, weights resident in shared memory
+//   reverse_batch lane sums (dexopt/src/ops.h:22-34)   dW = X^T G accumulated in registers over all frames and
+//                                                      rollouts of the CTA, one deterministic cross-CTA sum at the end
+//
+// Mapping: a CTA holds NW rollouts, one warp each (lane = joint / policy output / contact side inside a
+// phase, __syncwarp between phases); at the policy layers the NW warps turn into tile workers of one
+// [8 x n_in] x [n_in x n_out] product (M = the rollouts).  HBM sees the checkpoint (written once, read once),
+// the weights (once per CTA) and the per-CTA partial gradient.
+//
+// sm_100a only; no CPU path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/trx_b200.h"
+#include "assembly/dexsyn_options.h"
+#include "rollout/rollout_frame.h"
+#include "trx_rollout.h"
+
+using namespace rollout;
+
+namespace {
+
+struct KHeader {
+  int32_t v[H_COUNT];
+};
+
+struct KArgs {
+  const int32_t *I;  // plan integer tables (header included), ni words
+  const double *D;   // plan double tables, nd doubles
+  const double *x;   // policy parameters
+  const double *params;  // [3][R] per-rollout parameters (object start offset x, y, yaw)
+  double *ckpt;      // [chunk rollouts (padded)][frames][ckpt doubles]
+  double *partial;   // [grid][1 + nx]: loss and gradient partial of each CTA
+  double *r_out;     // residual vector (wide layout: scalar rows, then [row][R]) or null
+  const double *seed;  // adjoint seeds in the same layout, or null (seeds are the residuals)
+  long R;            // rollouts of the whole objective (stride of r_out / params)
+  long first;        // first rollout of this launch (chunk)
+  long count;        // rollouts of this launch
+  int ni, nd, nx;
+  int frames, n_groups, want_grad, accumulate;
+  // shared-memory layout, in doubles
+  int o_D, o_I, o_W1, o_B1, o_W2, o_B2, s_W1, s_W2, r_W1, r_W2;
+  int o_X, o_H, o_A, o_O, o_GX, o_GH, o_GO, s_X, s_H, s_O;
+  int o_tile, o_red, o_region;
+  int n_tiles, tiles_j1, tiles_1;  // dW tiles: [0, tiles_1) layer 1, rest layer 2
+};
+
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): g = lane >> 2, t = lane & 3;
+// A (8x4, row) a = A[g][t], B (4x8, col) b = B[t][g], C (8x8) c0, c1 = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Y[g][n] = sum_k X[g][k] W[k][n] + bias[n]   for the 8 rollout rows g; output tiles of 8 columns over the warps
+__device__ __forceinline__ void denseForward(const double *X, int sX, const double *W, int sW, const double *bias,
+                                             double *Y, int sY, int k_pad, int n_out, int warp, int n_warps, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int n0 = warp * 8; n0 < n_out; n0 += n_warps * 8) {
+    double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+    const double *xa = X + g * sX + t, *wb = W + t * sW + n0 + g;
+    int k = 0;
+    for (; k + 8 <= k_pad; k += 8) {
+      dmma884(c0, c1, xa[k], wb[k * sW]);
+      dmma884(d0, d1, xa[k + 4], wb[(k + 4) * sW]);
+    }
+    if (k < k_pad) dmma884(c0, c1, xa[k], wb[k * sW]);
+    Y[g * sY + n0 + 2 * t] = (c0 + d0) + bias[n0 + 2 * t];
+    Y[g * sY + n0 + 2 * t + 1] = (c1 + d1) + bias[n0 + 2 * t + 1];
+  }
+}
+
+// GX[g][i] = sum_j GY[g][j] W[i][j]
+__device__ __forceinline__ void denseBackwardX(const double *GY, int sY, const double *W, int sW, double *GX, int sX,
+                                               int k_pad, int n_in, int warp, int n_warps, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int i0 = warp * 8; i0 < n_in; i0 += n_warps * 8) {
+    double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+    const double *ya = GY + g * sY + t, *wb = W + (i0 + g) * sW + t;
+    int k = 0;
+    for (; k + 8 <= k_pad; k += 8) {
+      dmma884(c0, c1, ya[k], wb[k]);
+      dmma884(d0, d1, ya[k + 4], wb[k + 4]);
+    }
+    if (k < k_pad) dmma884(c0, c1, ya[k], wb[k]);
+    GX[g * sX + i0 + 2 * t] = c0 + d0;
+    GX[g * sX + i0 + 2 * t + 1] = c1 + d1;
+  }
+}
+
+template <int NW, int MAXT>
+__global__ void __launch_bounds__(NW * 32, 1)
+    trx_rollout_kernel(const __grid_constant__ KHeader hdr, const __grid_constant__ KArgs a) {
+  extern __shared__ double sm[];
+  const int32_t *H = hdr.v;
+  const int tid = threadIdx.x, nt = NW * 32, warp = tid >> 5, lane = tid & 31;
+  const int n_in = H[H_NIN], n_hid = H[H_NHID], n_out = H[H_NOUT], n_layers = H[H_NLAYERS], L = H[H_NLEVELS];
+  const int n1 = n_layers == 2 ? n_hid : n_out;  // output width of the first layer
+
+  // ---- stage the plan and the weights
+  double *sD = sm + a.o_D;
+  int32_t *sI = reinterpret_cast<int32_t *>(sm + a.o_I);
+  for (int e = tid; e < a.nd; e += nt) sD[e] = a.D[e];
+  for (int e = tid; e < a.ni; e += nt) sI[e] = a.I[e];
+  for (int e = tid; e < a.o_region - a.o_W1; e += nt) sm[a.o_W1 + e] = 0.0;  // weights (padded), activations, tables
+  __syncthreads();
+  if (n_layers) {
+    const double *W1 = a.x + H[H_W1], *B1 = a.x + H[H_B1];
+    for (int e = tid; e < n_in * n1; e += nt) {
+      int i = e / n1, j = e - i * n1;
+      sm[a.o_W1 + i * a.s_W1 + j] = W1[e];
+    }
+    for (int e = tid; e < n1; e += nt) sm[a.o_B1 + e] = B1[e];
+    if (n_layers == 2) {
+      const double *W2 = a.x + H[H_W2], *B2 = a.x + H[H_B2];
+      for (int e = tid; e < n_hid * n_out; e += nt) {
+        int i = e / n_out, j = e - i * n_out;
+        sm[a.o_W2 + i * a.s_W2 + j] = W2[e];
+      }
+      for (int e = tid; e < n_out; e += nt) sm[a.o_B2 + e] = B2[e];
+    }
+  }
+  // dW tile table: per tile {offset of the A operand column block, offset of the B operand column block}
+  int32_t *tile_tab = reinterpret_cast<int32_t *>(sm + a.o_tile);
+  for (int tl = tid; tl < a.n_tiles; tl += nt) {
+    int ti, tj, xo, yo;
+    if (tl < a.tiles_1) {
+      ti = tl / a.tiles_j1, tj = tl - ti * a.tiles_j1;
+      xo = a.o_X, yo = n_layers == 2 ? a.o_GH : a.o_GO;
+    } else {
+      const int tiles_j2 = (n_out + 7) >> 3;
+      ti = (tl - a.tiles_1) / tiles_j2, tj = (tl - a.tiles_1) - ti * tiles_j2;
+      xo = a.o_A, yo = a.o_GO;
+    }
+    tile_tab[2 * tl] = xo + ti * 8;
+    tile_tab[2 * tl + 1] = yo + tj * 8;
+  }
+  __syncthreads();
+
+  const double *sW1 = sm + a.o_W1, *sB1 = sm + a.o_B1, *sW2 = sm + a.o_W2, *sB2 = sm + a.o_B2;
+  double *XS = sm + a.o_X, *HS = sm + a.o_H, *AS = sm + a.o_A, *OS = sm + a.o_O;
+  double *GXS = sm + a.o_GX, *GHS = sm + a.o_GH, *GOS = sm + a.o_GO;
+  const int k1 = (n_in + 3) & ~3, k2 = (n_hid + 3) & ~3;
+  const int s1x = a.s_X;                                   // row stride of the first layer's input
+  const int s1y = n_layers == 2 ? a.s_H : a.s_O;           // and of its output / output adjoint
+  double *Y1 = n_layers == 2 ? HS : OS, *GY1 = n_layers == 2 ? GHS : GOS;
+
+  Ctx c;
+  c.H = H;
+  c.I = sI;
+  c.D = sD;
+  c.s = sm + a.o_region + warp * H[H_REGION];
+  c.x = XS + warp * a.s_X, c.h = HS + warp * a.s_H, c.a = AS + warp * a.s_H, c.out = OS + warp * a.s_O;
+  c.gx = GXS + warp * a.s_X, c.gh = GHS + warp * a.s_H, c.gout = GOS + warp * a.s_O;
+  c.r_stride = a.R;
+  c.frames = a.frames;
+  const int T = a.frames, CK = H[H_CKPT];
+
+  double loss = 0.0;
+  double acc[MAXT > 0 ? MAXT : 1][2];
+#pragma unroll
+  for (int u = 0; u < (MAXT > 0 ? MAXT : 1); u++) acc[u][0] = acc[u][1] = 0.0;
+  double gb0 = 0.0, gb1 = 0.0;  // bias gradients: element tid and tid + nt of {b1, b2}
+
+  // the frame's forward phases for this warp's rollout; recompute: values only (adjoint sweep)
+  auto forwardFrame = [&](const Ctx &cc, int f, bool active, double &ls, bool recompute) {
+    if (active) {
+      phaseSim(cc, lane);
+      __syncwarp();
+      for (int lv = 1; lv <= L; lv++) {
+        phaseChain(cc, lane, lv);
+        __syncwarp();
+      }
+      phaseObserve(cc, lane, f, ls);
+    }
+    if (!n_layers) return;
+    __syncthreads();
+    denseForward(XS, s1x, sW1, a.s_W1, sB1, Y1, s1y, k1, n1, warp, NW, lane);
+    __syncthreads();
+    if (n_layers == 2) {
+      if (active) phaseHidden(cc, lane, f, ls);
+      __syncthreads();
+      denseForward(AS, a.s_H, sW2, a.s_W2, sB2, OS, a.s_O, k2, n_out, warp, NW, lane);
+      __syncthreads();
+    }
+    if (active) {
+      phaseControl(cc, lane, f, ls);
+      __syncwarp();
+      phaseContact1(cc, lane, f, ls);
+      __syncwarp();
+      phaseContact2(cc, lane, f);
+      __syncwarp();
+      if (!recompute) {
+        phaseContact3(cc, lane, f, ls);
+        __syncwarp();
+        phaseContactSum(cc, lane);
+        __syncwarp();
+      }
+    }
+  };
+
+  for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+    const long local = (long)grp * NW + warp;  // rollout inside this launch
+    const bool active = local < a.count;
+    const long rollout = a.first + local;
+    double *ckpt = a.ckpt + (size_t)local * T * CK;
+    c.r_out = (a.r_out && active) ? a.r_out + H[H_NSCALAR] + rollout : nullptr;
+    c.seed = nullptr;
+    if (!active) {
+      // an idle warp of the last group: its rows of the activation matrices must stay zero
+      for (int e = lane; e < a.s_X; e += 32) c.x[e] = 0.0, c.gx[e] = 0.0;
+      for (int e = lane; e < a.s_H; e += 32) c.h[e] = 0.0, c.a[e] = 0.0, c.gh[e] = 0.0;
+      for (int e = lane; e < a.s_O; e += 32) c.out[e] = 0.0, c.gout[e] = 0.0;
+    }
+    // ---- forward sweep
+    if (active) {
+      const double pr[3] = {a.params[rollout], a.params[a.R + rollout], a.params[2 * a.R + rollout]};
+      phaseInit(c, lane, pr);
+      __syncwarp();
+      for (int lv = 1; lv <= L; lv++) {
+        phaseChain(c, lane, lv);
+        __syncwarp();
+      }
+    }
+    for (int f = 0; f < T; f++) {
+      if (active) {
+        phaseBeginFrame(c, lane, ckpt + (size_t)f * CK);
+        __syncwarp();
+      }
+      forwardFrame(c, f, active, loss, false);
+    }
+    if (active) {
+      phaseTerminal(c, lane, loss);
+      __syncwarp();
+    }
+    if (!a.want_grad) continue;
+
+    // ---- adjoint sweep
+    Ctx cb = c;
+    cb.r_out = nullptr;
+    cb.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
+    double unused = 0.0;
+    if (active) {
+      bphaseInit(cb, lane);
+      __syncwarp();
+    }
+    for (int f = T - 1; f >= 0; f--) {
+      const double *ck = ckpt + (size_t)f * CK;
+      if (active) {
+        phaseLoadCheckpoint(cb, lane, ck);
+        __syncwarp();
+      }
+      forwardFrame(cb, f, active, unused, true);
+      if (active) {
+        bphaseBegin(cb, lane, f);
+        __syncwarp();
+        bphaseBegin2(cb, lane, f);
+        __syncwarp();
+        if (n_layers) {
+          bphaseContact3(cb, lane, f);
+          __syncwarp();
+          bphaseContact2(cb, lane, f);
+          __syncwarp();
+          bphaseContact1(cb, lane, f);
+          __syncwarp();
+          bphaseControl(cb, lane, f);
+        }
+      }
+      if (n_layers) {
+        __syncthreads();
+        // adjoint of the last layer: input adjoint, then dW (register tiles) and db
+        if (n_layers == 2) denseBackwardX(GOS, a.s_O, sW2, a.s_W2, GHS, a.s_H, (n_out + 3) & ~3, n_hid, warp, NW, lane);
+        else denseBackwardX(GOS, a.s_O, sW1, a.s_W1, GXS, a.s_X, (n_out + 3) & ~3, n_in, warp, NW, lane);
+        if (MAXT > 0) {
+          const int gi = lane >> 2, t4 = lane & 3;
+#pragma unroll
+          for (int u = 0; u < MAXT; u++) {
+            const int tl = warp + u * NW;
+            // with two layers the first layer's tiles wait for its output adjoint (below)
+            if (tl < a.n_tiles && (n_layers == 1 || tl >= a.tiles_1)) {
+              const int sx = tl < a.tiles_1 ? a.s_X : a.s_H, sy = a.s_O;
+              const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
+              dmma884(acc[u][0], acc[u][1], xa[t4 * sx], yb[t4 * sy]);
+              dmma884(acc[u][0], acc[u][1], xa[(t4 + 4) * sx], yb[(t4 + 4) * sy]);
+            }
+          }
+        }
+        {
+          // db of the last layer: element e of {b1, b2} lives in thread e (mod nt)
+          const int base = n_layers == 2 ? n_hid : 0;
+          for (int e = tid, slot = 0; e < base + n_out; e += nt, slot++) {
+            if (e < base) continue;
+            const double *gy = GOS + (e - base);
+            double sgy = 0;
+            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_O];
+            if (slot == 0) gb0 += sgy;
+            else gb1 += sgy;
+          }
+        }
+        __syncthreads();
+        if (n_layers == 2) {
+          if (active) bphaseHidden(cb, lane, f);
+          __syncthreads();
+          denseBackwardX(GHS, a.s_H, sW1, a.s_W1, GXS, a.s_X, k2, n_in, warp, NW, lane);
+          if (MAXT > 0) {
+            const int gi = lane >> 2, t4 = lane & 3;
+#pragma unroll
+            for (int u = 0; u < MAXT; u++) {
+              const int tl = warp + u * NW;
+              if (tl < a.tiles_1) {
+                const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
+                dmma884(acc[u][0], acc[u][1], xa[t4 * a.s_X], yb[t4 * a.s_H]);
+                dmma884(acc[u][0], acc[u][1], xa[(t4 + 4) * a.s_X], yb[(t4 + 4) * a.s_H]);
+              }
+            }
+          }
+          for (int e = tid, slot = 0; e < n_hid; e += nt, slot++) {
+            const double *gy = GHS + e;
+            double sgy = 0;
+            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_H];
+            if (slot == 0) gb0 += sgy;
+            else gb1 += sgy;
+          }
+          __syncthreads();
+        }
+      }
+      if (active) {
+        bphaseObserve(cb, lane, f);
+        __syncwarp();
+        for (int lv = L; lv >= 1; lv--) {
+          bphaseChain(cb, lane, lv);
+          __syncwarp();
+        }
+        bphaseSim(cb, lane, ck);
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- this CTA's partial loss and gradient
+  double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
+  {
+    for (int off = 16; off > 0; off >>= 1) loss += __shfl_down_sync(0xffffffffu, loss, off);
+    double *red = sm + a.o_red;
+    __syncthreads();
+    if (lane == 0) red[warp] = loss;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0;
+      for (int w = 0; w < NW; w++) s += red[w];
+      part[0] = a.accumulate ? part[0] + s : s;
+    }
+  }
+  if (a.want_grad && n_layers) {
+    const int gi = lane >> 2, t4 = lane & 3;
+    if (MAXT > 0) {
+#pragma unroll
+      for (int u = 0; u < MAXT; u++) {
+        const int tl = warp + u * NW;
+        if (tl >= a.n_tiles) continue;
+        int ti, tj, base, width, rows;
+        if (tl < a.tiles_1) {
+          ti = tl / a.tiles_j1, tj = tl - ti * a.tiles_j1;
+          base = H[H_W1], width = n1, rows = n_in;
+        } else {
+          const int tiles_j2 = (n_out + 7) >> 3;
+          ti = (tl - a.tiles_1) / tiles_j2, tj = (tl - a.tiles_1) - ti * tiles_j2;
+          base = H[H_W2], width = n_out, rows = n_hid;
+        }
+        const int i = ti * 8 + gi, j = tj * 8 + 2 * t4;
+        if (i < rows) {
+          double *p = part + 1 + base + i * width + j;
+          if (j < width) p[0] = a.accumulate ? p[0] + acc[u][0] : acc[u][0];
+          if (j + 1 < width) p[1] = a.accumulate ? p[1] + acc[u][1] : acc[u][1];
+        }
+      }
+    }
+    const int nb = (n_layers == 2 ? n_hid : 0) + n_out;
+    for (int e = tid, slot = 0; e < nb; e += nt, slot++) {
+      const double v = slot == 0 ? gb0 : gb1;
+      // {b1, b2} order; with one layer the only bias is b1
+      const int idx = n_layers == 2 ? (e < n_hid ? H[H_B1] + e : H[H_B2] + (e - n_hid)) : H[H_B1] + e;
+      part[1 + idx] = a.accumulate ? part[1 + idx] + v : v;
+    }
+  }
+}
+
+// deterministic cross-CTA sum: out[0] = loss, out[1 + i] = gradient; the lane-independent weight-decay rows
+// (neural.h:159-171: r = reg * w) are added here, once, when this rank owns them
+__global__ void trx_rollout_reduce_kernel(const double *__restrict__ partial, int n_parts, int nx,
+                                          const double *__restrict__ x, double reg, int scalar_rows, int want_grad,
+                                          const double *__restrict__ seed, double *__restrict__ r_out,
+                                          double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (want_grad && i < nx) {
+    double s = 0;
+    for (int p = 0; p < n_parts; p++) s += partial[(size_t)p * (1 + nx) + 1 + i];
+    if (scalar_rows) s += (seed ? seed[i] : x[i] * reg) * reg;
+    out[1 + i] = s;
+  }
+  if (r_out && scalar_rows && i < nx) r_out[i] = x[i] * reg;
+  if (blockIdx.x == 0) {
+    __shared__ double red[256];
+    double s = 0;
+    if (scalar_rows)
+      for (int k = threadIdx.x; k < nx; k += blockDim.x) {
+        double v = x[k] * reg;
+        s += v * v;
+      }
+    for (int p = threadIdx.x; p < n_parts; p += blockDim.x) s += partial[(size_t)p * (1 + nx)];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+      if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+
+struct trx_rollout {
+  Plan plan;
+  KHeader hdr;
+  KArgs args;
+  int device = 0;
+  int nw = 8, maxt = 0, grid = 0;
+  size_t smem_bytes = 0;
+  uint64_t lanes = 0, chunk = 0, n_chunks = 0;
+  bool scalar_rows = true;
+  int32_t *d_I = nullptr;
+  double *d_D = nullptr, *d_params = nullptr, *d_ckpt = nullptr, *d_partial = nullptr;
+  uint64_t launches = 0;
+  double reg = 0;
+};
+
+namespace {
+
+typedef void (*KernelFn)(const KHeader, const KArgs);
+struct Variant {
+  int nw, maxt;
+  KernelFn fn;
+};
+#define RL_VARIANT(NW, MAXT) {NW, MAXT, trx_rollout_kernel<NW, MAXT>}
+const Variant kVariants[] = {RL_VARIANT(8, 8), RL_VARIANT(8, 18), RL_VARIANT(8, 28), RL_VARIANT(4, 28)};
+
+#define RL_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      err = std::string(#expr) + ": " + cudaGetErrorString(_e);                        \
+      return TRX_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+}  // namespace
+
+trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_device_bytes, int device,
+                            bool scalar_rows, trx_rollout **out, std::string &err) {
+  *out = nullptr;
+  std::unique_ptr<trx_rollout, void (*)(trx_rollout *)> ro(new trx_rollout(), trxRolloutDestroy);
+  try {
+    dexsyn::ProblemOptions po = dexsyn::parseProblemOptions(options);
+    if (po.outer != 1) {
+      err = "re-rolled objective: outer batches are replicas of the flat tape only (use more rollouts)";
+      return TRX_ERR_UNSUPPORTED;
+    }
+    ro->plan = makePlan(dexsyn::makeModel(po.model), dexsyn::EnvInfo(), po.frames);
+  } catch (const std::exception &e) {
+    err = e.what();
+    return TRX_ERR_INVALID;
+  }
+  if (!ro->plan.error.empty()) {
+    err = "re-rolled objective: " + ro->plan.error;
+    return TRX_ERR_UNSUPPORTED;
+  }
+  if (lanes == 0) {
+    err = "lanes must be positive";
+    return TRX_ERR_INVALID;
+  }
+  const auto &I = ro->plan.i;
+  if (I[H_NLAYERS] == 0 || I[H_NX] == 0) {
+    err = "re-rolled objective: no policy, nothing to differentiate";
+    return TRX_ERR_UNSUPPORTED;
+  }
+  std::memcpy(ro->hdr.v, I.data(), sizeof(ro->hdr.v));
+  ro->device = device;
+  ro->lanes = lanes;
+  ro->scalar_rows = scalar_rows;
+  ro->reg = ro->plan.d[I[H_D_CONST] + DC_W_REG];
+  RL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RL_CUDA(cudaGetDeviceProperties(&prop, device));
+
+  // ---- shared-memory layout and kernel variant
+  KArgs &a = ro->args;
+  std::memset(&a, 0, sizeof(a));
+  const int n_in = I[H_NIN], n_hid = I[H_NHID], n_out = I[H_NOUT], n_layers = I[H_NLAYERS];
+  const int n1 = n_layers == 2 ? n_hid : n_out;
+  a.ni = (int)I.size();
+  a.nd = (int)ro->plan.d.size();
+  a.nx = I[H_NX];
+  a.frames = ro->plan.frames;
+  a.tiles_j1 = (n1 + 7) / 8;
+  a.tiles_1 = ((n_in + 7) / 8) * a.tiles_j1;
+  a.n_tiles = a.tiles_1 + (n_layers == 2 ? ((n_hid + 7) / 8) * ((n_out + 7) / 8) : 0);
+  const Variant *pick = nullptr;
+  for (const Variant &v : kVariants) {
+    int off = 0;
+    auto take = [&](int n) {
+      int o = off;
+      off += padTo(n, 2);
+      return o;
+    };
+    a.o_D = take(a.nd);
+    a.o_I = take((a.ni + 1) / 2);
+    a.s_W1 = fragStride(n1);
+    a.r_W1 = padTo(n_in, 8);
+    a.o_W1 = take(a.r_W1 * a.s_W1);
+    a.o_B1 = take(a.s_W1);
+    a.s_W2 = n_layers == 2 ? fragStride(n_out) : 0;
+    a.r_W2 = n_layers == 2 ? padTo(n_hid, 8) : 0;
+    a.o_W2 = take(a.r_W2 * a.s_W2);
+    a.o_B2 = take(a.s_W2);
+    a.s_X = fragStride(n_in);
+    a.s_H = n_layers == 2 ? fragStride(n_hid) : 0;
+    a.s_O = fragStride(n_out);
+    a.o_X = take(8 * a.s_X);
+    a.o_H = take(8 * a.s_H);
+    a.o_A = take(8 * a.s_H);
+    a.o_O = take(8 * a.s_O);
+    a.o_GX = take(8 * a.s_X);
+    a.o_GH = take(8 * a.s_H);
+    a.o_GO = take(8 * a.s_O);
+    a.o_tile = take(a.n_tiles);
+    a.o_red = take(8);
+    a.o_region = off;
+    off += v.nw * I[H_REGION];
+    size_t bytes = (size_t)off * sizeof(double);
+    if ((a.n_tiles + v.nw - 1) / v.nw > v.maxt) continue;
+    if (bytes > (size_t)prop.sharedMemPerBlockOptin) continue;
+    if ((n_layers == 2 ? n_hid : 0) + n_out > 2 * v.nw * 32) continue;  // bias gradients: two per thread
+    pick = &v;
+    ro->smem_bytes = bytes;
+    break;
+  }
+  if (!pick) {
+    err = "re-rolled objective: policy layers of this size do not fit the kernel variants (shared memory / tiles per warp)";
+    return TRX_ERR_UNSUPPORTED;
+  }
+  ro->nw = pick->nw;
+  ro->maxt = pick->maxt;
+  RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
+
+  // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
+  const uint64_t ck_bytes_per_rollout = (uint64_t)a.frames * I[H_CKPT] * sizeof(double);
+  uint64_t chunk = lanes;
+  if (max_device_bytes && chunk * ck_bytes_per_rollout > max_device_bytes)
+    chunk = std::max<uint64_t>(ro->nw, max_device_bytes / ck_bytes_per_rollout / ro->nw * ro->nw);
+  ro->chunk = chunk;
+  ro->n_chunks = (lanes + chunk - 1) / chunk;
+  const uint64_t groups = (chunk + ro->nw - 1) / ro->nw;
+  ro->grid = (int)std::min<uint64_t>(groups, (uint64_t)prop.multiProcessorCount);
+  RL_CUDA(cudaMalloc(&ro->d_I, I.size() * sizeof(int32_t)));
+  RL_CUDA(cudaMemcpy(ro->d_I, I.data(), I.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  RL_CUDA(cudaMalloc(&ro->d_D, ro->plan.d.size() * sizeof(double)));
+  RL_CUDA(cudaMemcpy(ro->d_D, ro->plan.d.data(), ro->plan.d.size() * sizeof(double), cudaMemcpyHostToDevice));
+  RL_CUDA(cudaMalloc(&ro->d_params, 3 * lanes * sizeof(double)));
+  RL_CUDA(cudaMemset(ro->d_params, 0, 3 * lanes * sizeof(double)));
+  RL_CUDA(cudaMalloc(&ro->d_ckpt, groups * ro->nw * ck_bytes_per_rollout));
+  RL_CUDA(cudaMalloc(&ro->d_partial, (size_t)ro->grid * (1 + a.nx) * sizeof(double)));
+  RL_CUDA(cudaMemset(ro->d_partial, 0, (size_t)ro->grid * (1 + a.nx) * sizeof(double)));
+  a.I = ro->d_I;
+  a.D = ro->d_D;
+  a.params = ro->d_params;
+  a.ckpt = ro->d_ckpt;
+  a.partial = ro->d_partial;
+  a.R = (long)lanes;
+  *out = ro.release();
+  return TRX_OK;
+}
+
+void trxRolloutDestroy(trx_rollout *ro) {
+  if (!ro) return;
+  cudaFree(ro->d_I);
+  cudaFree(ro->d_D);
+  cudaFree(ro->d_params);
+  cudaFree(ro->d_ckpt);
+  cudaFree(ro->d_partial);
+  delete ro;
+}
+
+uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key) {
+  const auto &I = ro->plan.i;
+  std::string k = key;
+  if (k == "n_x") return I[H_NX];
+  if (k == "parameter_elems") return 3 * ro->lanes;
+  if (k == "chunk_lanes") return ro->chunk;
+  if (k == "n_chunks") return ro->n_chunks;
+  if (k == "device_bytes")
+    return (uint64_t)((ro->chunk + ro->nw - 1) / ro->nw * ro->nw) * ro->plan.frames * I[H_CKPT] * 8 +
+           (uint64_t)ro->grid * (1 + I[H_NX]) * 8 + 3 * ro->lanes * 8;
+  if (k == "launches_per_evaluation") return ro->n_chunks + 1;
+  if (k == "residual_elems") return (uint64_t)I[H_NSCALAR] + ((uint64_t)ro->plan.frames * I[H_ROWS_FRAME] + 6) * ro->lanes;
+  if (k == "n_scalar_rows") return I[H_NSCALAR];
+  if (k == "rows_per_frame") return I[H_ROWS_FRAME];
+  if (k == "checkpoint_bytes_per_unit") return (uint64_t)I[H_CKPT] * 8;
+  if (k == "rollouts_per_cta") return ro->nw;
+  if (k == "grid") return ro->grid;
+  if (k == "shared_bytes") return ro->smem_bytes;
+  if (k == "tiles_per_warp") return ro->maxt;
+  if (k == "n_joints") return I[H_NJ];
+  if (k == "n_levels") return I[H_NLEVELS];
+  if (k == "n_controlled") return I[H_NQ];
+  if (k == "n_end_effectors") return I[H_NEE];
+  if (k == "n_in") return I[H_NIN];
+  if (k == "n_hidden") return I[H_NHID];
+  if (k == "n_out") return I[H_NOUT];
+  return ~0ull;
+}
+
+trx_status trxRolloutParameterize(trx_rollout *ro, const void *packed, uint64_t bytes, cudaStream_t stream,
+                                  std::string &err) {
+  if (bytes != 3 * ro->lanes * sizeof(double)) {
+    err = "packed buffer size mismatch: got " + std::to_string(bytes) + " expected " +
+          std::to_string(3 * ro->lanes * sizeof(double));
+    return TRX_ERR_SIZE;
+  }
+  RL_CUDA(cudaSetDevice(ro->device));
+  RL_CUDA(cudaMemcpyAsync(ro->d_params, packed, bytes, cudaMemcpyHostToDevice, stream));
+  RL_CUDA(cudaStreamSynchronize(stream));
+  return TRX_OK;
+}
+
+// d_out = {loss, gradient[n_x]} (want_grad) or {loss}; d_r: residual vector in the wide layout or null;
+// d_seed: adjoint seeds in the same layout or null
+trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out, double *d_r, const double *d_seed,
+                              bool want_grad, cudaStream_t stream, std::string &err) {
+  RL_CUDA(cudaSetDevice(ro->device));
+  KernelFn fn = nullptr;
+  for (const Variant &v : kVariants)
+    if (v.nw == ro->nw && v.maxt == ro->maxt) fn = v.fn;
+  KArgs a = ro->args;
+  a.x = d_x;
+  a.r_out = d_r;
+  a.seed = d_seed;
+  a.want_grad = want_grad ? 1 : 0;
+  for (uint64_t ch = 0; ch < ro->n_chunks; ch++) {
+    a.first = (long)(ch * ro->chunk);
+    a.count = (long)std::min<uint64_t>(ro->chunk, ro->lanes - ch * ro->chunk);
+    a.n_groups = (int)((a.count + ro->nw - 1) / ro->nw);
+    a.accumulate = ch > 0 ? 1 : 0;
+    // every CTA of the grid writes its partial slot, also when it has no group in this chunk
+    fn<<<ro->grid, ro->nw * 32, ro->smem_bytes, stream>>>(ro->hdr, a);
+    ro->launches++;
+  }
+  const int nx = ro->args.nx;
+  trx_rollout_reduce_kernel<<<(nx + 255) / 256, 256, 0, stream>>>(ro->d_partial, ro->grid, nx, d_x, ro->reg,
+                                                                    ro->scalar_rows ? 1 : 0, want_grad ? 1 : 0, d_seed,
+                                                                    d_r, d_out);
+  ro->launches++;
+  RL_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+uint64_t trxRolloutLaunches(const trx_rollout *ro) { return ro->launches; }

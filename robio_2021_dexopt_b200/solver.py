@@ -95,6 +95,37 @@ class Objective:
             pass
 
 
+class RolloutObjective(Objective):
+    """The same objective in re-rolled form (trx_objective_create_rollout): one frame program and the carried
+    state instead of a flat tape, evaluated by the hand-written forward / adjoint frame kernels
+    (csrc/trx_rollout.cu).  Built from the problem description that build_dexsyn takes; per-rollout
+    parameters are [3][lanes] = object start offset x, y and yaw (dexenv_grasp.h:149-165)."""
+
+    def __init__(self, engine: CudaEngine, lanes: int, max_device_bytes: int = 0, scalar_rows: bool = True,
+                 **options):
+        self.engine = engine
+        self._h = ctypes.c_void_p()
+        self.options = " ".join("%s=%s" % (k, v) for k, v in options.items())
+        L = _native.lib()
+        L.trx_objective_create_rollout.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.trx_objective_residuals.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                              ctypes.c_void_p]
+        check(L.trx_objective_create_rollout(self.options.encode(), lanes, max_device_bytes, engine.device,
+                                             0 if scalar_rows else 2, ctypes.byref(self._h)))
+        self.lanes = lanes
+        self.n_x = self.info("n_x")
+        self._g = np.empty(self.n_x)
+
+    def residuals(self, x: np.ndarray) -> np.ndarray:
+        """r = x_prog->run(x): lane-independent rows once, then [row][rollout]"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.n_x
+        r = np.empty(self.info("residual_elems"))
+        check(_native.lib().trx_objective_residuals(self._h, x.ctypes.data, r.ctypes.data, r.nbytes, None))
+        return r
+
+
 class GradientDescentSolver:
     """GradientDescentSolver (solvers/gd.h:14-129): momentum gradient descent on J^T r."""
 

@@ -16,4 +16,10 @@ $R record /tmp/dexsyn_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_
 $R record /tmp/dexsyn_dropout_outer2.trxb problem=dexsyn frames=2 hidden=4 tiles=2 extra_fixed=2 dropout=1 outer=2 gd_steps=10
 xz -9 -f -c /tmp/dexsyn_small.trxb > $G/dexsyn_small.trxb.xz
 xz -9 -f -c /tmp/dexsyn_dropout_outer2.trxb > $G/dexsyn_dropout_outer2.trxb.xz
+# values-only fixtures (programs=0) for the re-rolled rollout objective at BASELINE's shapes: the product
+# records / assembles these problems itself (trx_dexsyn_build, trx_objective_create_rollout)
+$R record $G/rollout_handarm_h64.trxb problem=dexsyn kind=handarm hidden=64 frames=4 tiles=2 gd_steps=10 programs=0 gd_keep=last keep_dr=0
+$R record $G/rollout_hand8_linear.trxb problem=dexsyn kind=hand8 hidden=0 frames=5 tiles=2 gd_steps=10 programs=0 gd_keep=last keep_dr=0
+$R record $G/rollout_chain30.trxb problem=dexsyn kind=chain joints=30 contacts=16 hidden=16 frames=3 tiles=1 programs=0 keep_dr=0
+$R record $G/rollout_handarm_long.trxb problem=dexsyn kind=handarm hidden=8 frames=24 tiles=1 programs=0 keep_dr=0
 ls -la $G
