@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtrx_b200.so")
+# TRX_B200_LIB: development builds of the same library (e.g. with per-phase clocks); never a different engine
+LIB_PATH = os.environ.get("TRX_B200_LIB") or os.path.join(_HERE, "libtrx_b200.so")
 
 _lib = None
 

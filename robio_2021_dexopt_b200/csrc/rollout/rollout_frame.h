@@ -60,6 +60,7 @@ struct Ctx {
   const double *seed;  // adjoint seeds by residual row (null: the residuals themselves, g = J^T r)
   long r_stride;
   int frames;
+  bool emit;         // false: values only (the adjoint sweep recomputes a frame without counting it again)
 };
 
 // ---- small load/store helpers
@@ -79,6 +80,7 @@ RL_HD const double *dconst(const Ctx &c) { return c.D + c.H[H_D_CONST]; }
 
 // residual row: value into the loss (and the residual vector when asked for)
 RL_HD void emit(const Ctx &c, long row, double v, double &loss) {
+  if (!c.emit) return;
   loss += v * v;
   if (c.r_out) c.r_out[row * c.r_stride] = v;
 }
@@ -103,36 +105,40 @@ RL_HD TwistV pinvReverse(const PoseV &p, const PoseV &inv, const TwistV &g_inv) 
 
 // ================================================================================== forward phases
 
-// start of a forward frame: the link poses of the previous frame become "previous" (physics5.h:577), and the
-// carried state is checkpointed
-RL_HD void phaseBeginFrame(const Ctx &c, int lane, double *ckpt) {
+// start of a forward frame: the contact impulses of the previous frame reach the momenta (applyForce,
+// physics5.h:114-121,672-675, in end-effector order), the link poses of the previous frame become "previous"
+// (physics5.h:577), and the carried state {q, commands, body, previous poses} is checkpointed -- one contiguous copy
+RL_HD void phaseBeginFrame(const Ctx &c, int lane, int frame, double *ckpt) {
   const int32_t *I = c.I, *H = c.H;
   const int nq = H[H_NQ], nt = H[H_NTRACK];
   double *s = c.s;
-  for (int e = lane; e < nq; e += 32) {
-    ckpt[e] = s[H[R_Q] + e];
-    ckpt[nq + e] = s[H[R_CMD] + e];
+  double *carried = s + H[R_Q];
+  const int n_state = 2 * nq + B_COUNT;
+  for (int e = lane; e < n_state; e += 32) {
+    double v = carried[e];
+    const int m = e - (2 * nq + B_LM);  // 0..5: linear, angular momentum components
+    if (m >= 0 && frame > 0) {
+      for (int ee = 0; ee < H[H_NEE]; ee++) v += s[H[R_EE] + ee * EE_STRIDE + EE_IMP + m];
+      carried[e] = v;
+    }
+    ckpt[e] = v;
   }
-  for (int e = lane; e < B_COUNT; e += 32) ckpt[2 * nq + e] = s[H[R_BODY] + e];
   for (int e = lane; e < nt * 7; e += 32) {
-    int t = e / 7, k = I[H[H_I_TRACK] + t];
-    double v = s[H[R_POSE] + k * 7 + (e - t * 7)];
-    s[H[R_PREV] + e] = v;
-    ckpt[2 * nq + B_COUNT + e] = v;
+    const int t = e / 7, k = I[H[H_I_TRACK] + t];
+    const double v = s[H[R_POSE] + k * 7 + (e - t * 7)];
+    carried[n_state + e] = v;
+    ckpt[n_state + e] = v;
   }
 }
 
-// start of an adjoint frame: restore the carried state the frame started from
-RL_HD void phaseLoadCheckpoint(const Ctx &c, int lane, const double *ckpt) {
-  const int32_t *I = c.I, *H = c.H;
-  const int nq = H[H_NQ], nt = H[H_NTRACK];
-  double *s = c.s;
-  for (int e = lane; e < nq; e += 32) {
-    s[H[R_Q] + e] = ckpt[e];
-    s[H[R_CMD] + e] = ckpt[nq + e];
-  }
-  for (int e = lane; e < B_COUNT; e += 32) s[H[R_BODY] + e] = ckpt[2 * nq + e];
-  for (int e = lane; e < nt * 7; e += 32) s[H[R_PREV] + e] = ckpt[2 * nq + B_COUNT + e];
+// start of an adjoint frame: restore the carried state the frame started from (values prefetched into
+// registers by the caller: pre[i] = ckpt[lane + 32 i])
+template <int N> RL_HD void phaseLoadCheckpoint(const Ctx &c, int lane, const double (&pre)[N]) {
+  double *carried = c.s + c.H[R_Q];
+  const int n = c.H[H_CKPT];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+    if (lane + 32 * i < n) carried[lane + 32 * i] = pre[i];
 }
 
 // intermediate values of the body step that both sweeps need
@@ -197,6 +203,7 @@ RL_HD void phaseSim(const Ctx &c, int lane) {
   if (lane == 31) {
     BodyStep b;
     double *body = s + H[R_BODY];
+    for (int e = 0; e < B_COUNT; e++) s[H[R_BODY0] + e] = body[e];  // the adjoint restarts from here
     bodyForward(dc, body, b);
     st3(s + H[R_CG], b.cg);
     st3(body + B_POS, b.pos2);
@@ -207,21 +214,23 @@ RL_HD void phaseSim(const Ctx &c, int lane) {
   }
 }
 
-// forward kinematics, one tree level: pose = parent * (origin.t, local rotation)
-RL_HD void phaseChain(const Ctx &c, int lane, int level) {
+// forward kinematics, one super-level: every lane walks one serial segment of the tree with the running pose
+// in registers, pose = parent * (origin.t, local rotation) joint after joint
+RL_HD void phaseChain(const Ctx &c, int lane, int super) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  const int k0 = I[H[H_I_LEVEL] + level - 1], k1 = I[H[H_I_LEVEL] + level];
-  for (int k = k0 + lane; k < k1; k += 32) {
-    const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
-    if (ji[JI_TYPE] == dexsyn::JOINT_FLOATING) continue;  // posed by the body lane
-    const double *jd = c.D + H[H_D_JOINT] + k * JD_STRIDE;
-    const PoseV parent = ldp(s + H[R_POSE] + ji[JI_PARENT] * 7);
-    const Q4 lr = ji[JI_TYPE] == dexsyn::JOINT_REVOLUTE ? ld4(s + H[R_LQ] + k * 4) : ld4(jd + JD_ORIGIN + 3);
-    PoseV p;
-    p.t = parent.t + qrot(parent.r, ld3(jd + JD_ORIGIN));
-    p.r = qmul(parent.r, lr);
-    stp(s + H[R_POSE] + k * 7, p);
+  const int s0 = I[H[H_I_SUPER] + super - 1], s1 = I[H[H_I_SUPER] + super];
+  for (int sg = s0 + lane; sg < s1; sg += 32) {
+    const int k0 = I[H[H_I_SEG] + 2 * sg], n = I[H[H_I_SEG] + 2 * sg + 1];
+    PoseV p = ldp(s + H[R_POSE] + I[H[H_I_JOINT] + k0 * JI_STRIDE + JI_PARENT] * 7);
+    const double *jd = c.D + H[H_D_JOINT] + k0 * JD_STRIDE;
+    const double *lq = s + H[R_LQ] + k0 * 4;
+    double *out = s + H[R_POSE] + k0 * 7;
+    for (int j = 0; j < n; j++, jd += JD_STRIDE, lq += 4, out += 7) {
+      p.t = p.t + qrot(p.r, ld3(jd + JD_ORIGIN));
+      p.r = qmul(p.r, ld4(lq));
+      stp(out, p);
+    }
   }
 }
 
@@ -367,8 +376,10 @@ RL_HD void phaseContact1(const Ctx &c, int lane, int frame, double &loss) {
     const PoseV pose = ldp(s + H[R_POSE] + sd.link * 7);
     const V3 pt = pmulv(pose, ld3(sd.sd + ED_CENTER)) + cs;
     st3(s + H[R_EE] + sd.e * EE_STRIDE + (sd.side ? EE_C2 : EE_C1), pt);
-    const V3 local = pmulv(pinv(pose), pt);
-    shapeRows<false>(c, sd.si, sd.sd, local, sd.row_shape, loss);
+    if (c.emit) {
+      const V3 local = pmulv(pinv(pose), pt);
+      shapeRows<false>(c, sd.si, sd.sd, local, sd.row_shape, loss);
+    }
   }
   // velocity-controller commands for the next frame (dexenv_grasp.h:200-219): coupling, scaling
   for (int ci = lane; ci < nq; ci += 32) {
@@ -426,25 +437,11 @@ RL_HD void phaseContact3(const Ctx &c, int lane, int frame, double &loss) {
       emit(c, row_t + 9 + 3 * k + 1, dv.y * f[k], loss);
       emit(c, row_t + 9 + 3 * k + 2, dv.z * f[k], loss);
     }
-    // applyForce (physics5.h:114-121,672-675): the momenta are updated by lane 31 in end-effector order
+    // applyForce (physics5.h:114-121,672-675): the momenta take these at the start of the next frame
     const V3 impulse = force * dc[DC_DT];
-    st3(ee + EE_GV1, impulse);  // adjoint scratch is free during a forward pass
-    st3(ee + EE_GV2, cross(c1 - ld3(s + H[R_CG]), impulse));
+    st3(ee + EE_IMP, impulse);
+    st3(ee + EE_IMP + 3, cross(c1 - ld3(s + H[R_CG]), impulse));
   }
-}
-
-RL_HD void phaseContactSum(const Ctx &c, int lane) {
-  const int32_t *I = c.I, *H = c.H;
-  double *s = c.s;
-  if (lane != 31) return;
-  V3 lm = ld3(s + H[R_BODY] + B_LM), am = ld3(s + H[R_BODY] + B_AM);
-  for (int e = 0; e < H[H_NEE]; e++) {
-    const double *ee = s + H[R_EE] + e * EE_STRIDE;
-    lm = lm + ld3(ee + EE_GV1);
-    am = am + ld3(ee + EE_GV2);
-  }
-  st3(s + H[R_BODY] + B_LM, lm);
-  st3(s + H[R_BODY] + B_AM, am);
 }
 
 // terminal goals: MoveGoal (goals.h:173-191) and RelativeOrientationGoal (goals.h:71-89)
@@ -481,6 +478,10 @@ RL_HD void phaseInit(const Ctx &c, int lane, const double *params) {
   double *s = c.s;
   const int nq = H[H_NQ];
   for (int e = lane; e < H[H_NSTATIC] * 7; e += 32) s[H[R_POSE] + e] = c.D[H[H_D_STATIC] + e];
+  // local rotation of a fixed joint: its origin's, for good
+  for (int k = lane; k < H[H_NJ]; k += 32)
+    if (I[H[H_I_JOINT] + k * JI_STRIDE + JI_TYPE] != dexsyn::JOINT_REVOLUTE)
+      st4(s + H[R_LQ] + k * 4, ld4(c.D + H[H_D_JOINT] + k * JD_STRIDE + JD_ORIGIN + 3));
   for (int ci = lane; ci < nq; ci += 32) {
     const double q = c.D[H[H_D_CTRL] + ci * CD_STRIDE + CD_Q0];
     s[H[R_Q] + ci] = q;
@@ -511,14 +512,18 @@ RL_HD void bphaseBegin(const Ctx &c, int lane, int frame) {
   for (int e = lane; e < nj * 6; e += 32) {
     const int k = e / 6;
     const int t = I[H[H_I_JOINT] + k * JI_STRIDE + JI_TRACK];
-    s[H[R_GPOSE] + e] = t >= 0 ? s[H[R_GPREV] + t * 6 + (e - k * 6)] : 0.0;
-    s[H[R_GC] + e] = 0.0;
+    double g = 0.0;
+    if (t >= 0) {
+      g = s[H[R_GPREV] + t * 6 + (e - k * 6)];
+      s[H[R_GPREV] + t * 6 + (e - k * 6)] = 0.0;  // refilled by this frame's slip velocities
+    }
+    s[H[R_GPOSE] + e] = g;
   }
 }
 RL_HD void bphaseBegin2(const Ctx &c, int lane, int frame) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  for (int e = lane; e < H[H_NTRACK] * 6; e += 32) s[H[R_GPREV] + e] = 0.0;
+  // first and last frame only: the terminal goals look at the object pose of both
   if (lane == 31) {
     if (frame == c.frames - 1) {
       // reverse of the terminal goals: reverse_mul_fg_vec3_s, reverse_sub_fg_vec3 (second operand negated),
@@ -739,38 +744,40 @@ RL_HD void bphaseObserve(const Ctx &c, int lane, int frame) {
   }
 }
 
-// adjoint of the forward kinematics, one tree level (deepest first): a joint collects what its children
-// left for it, hands its parent's share up and takes its own angle's share
+// adjoint of the forward kinematics, one super-level (deepest first): a lane walks its segment from the last
+// joint to the first; a joint collects what its own link and the segments hanging off it left, takes its angle's
+// share and hands the rest up
 // (reverse_mul_fg_pose: da = (dx.t, cross(qrot(a.r, b.t), dx.t) + dx.r);
 //  reverse_fg_pose_angle_axis_pose: dangle = dot(qrot(qinv(parent.r), dp.r), axis))
-RL_HD void bphaseChain(const Ctx &c, int lane, int level) {
+RL_HD void bphaseChain(const Ctx &c, int lane, int super) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  const int k0 = I[H[H_I_LEVEL] + level - 1], k1 = I[H[H_I_LEVEL] + level];
-  for (int k = k0 + lane; k < k1; k += 32) {
-    const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
-    TwistV g = ldt(s + H[R_GPOSE] + k * 6);
-    for (int ch = 0; ch < ji[JI_NCHILD]; ch++) {
-      const TwistV gc = ldt(s + H[R_GC] + I[ji[JI_CHILD0] + ch] * 6);
-      g.t = g.t + gc.t;
-      g.r = g.r + gc.r;
+  const int s0 = I[H[H_I_SUPER] + super - 1], s1 = I[H[H_I_SUPER] + super];
+  for (int sg = s0 + lane; sg < s1; sg += 32) {
+    const int k0 = I[H[H_I_SEG] + 2 * sg], n = I[H[H_I_SEG] + 2 * sg + 1];
+    TwistV carry{{0, 0, 0}, {0, 0, 0}};
+    for (int k = k0 + n - 1; k >= k0; k--) {
+      const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
+      TwistV g = ldt(s + H[R_GPOSE] + k * 6);
+      g.t = g.t + carry.t;
+      g.r = g.r + carry.r;
+      for (int ch = 0; ch < ji[JI_NCHILD]; ch++) {
+        const TwistV gc = ldt(s + H[R_GC] + I[ji[JI_CHILD0] + ch] * 6);
+        g.t = g.t + gc.t;
+        g.r = g.r + gc.r;
+      }
+      const PoseV parent = ldp(s + H[R_POSE] + (k > k0 ? k - 1 : ji[JI_PARENT]) * 7);
+      const V3 arm = ld3(s + H[R_POSE] + k * 7) - parent.t;  // = qrot(parent.r, origin.t)
+      carry = TwistV{g.t, cross(arm, g.t) + g.r};
+      // fixed joints carry a zero axis and the spare slot n_q
+      s[H[R_GQ] + ji[JI_CTRL]] += dot(qrot(qinv(parent.r), g.r), ld3(c.D + H[H_D_JOINT] + k * JD_STRIDE + JD_CAXIS));
     }
-    if (ji[JI_TYPE] == dexsyn::JOINT_FLOATING) {
-      stt(s + H[R_GPOSE] + k * 6, g);  // read by the body lane
-      continue;
-    }
-    const PoseV parent = ldp(s + H[R_POSE] + ji[JI_PARENT] * 7);
-    const V3 arm = ld3(s + H[R_POSE] + k * 7) - parent.t;  // = qrot(parent.r, origin.t)
-    stt(s + H[R_GC] + k * 6, TwistV{g.t, cross(arm, g.t) + g.r});
-    if (ji[JI_TYPE] == dexsyn::JOINT_REVOLUTE) {
-      const double *jd = c.D + H[H_D_JOINT] + k * JD_STRIDE;
-      s[H[R_GQ] + ji[JI_CTRL]] += dot(qrot(qinv(parent.r), g.r), ld3(jd + JD_CAXIS));
-    }
+    stt(s + H[R_GC] + k0 * 6, carry);
   }
 }
 
 // adjoint of the simulator step: velocity controllers (lanes < n_q) and the body (lane 31)
-RL_HD void bphaseSim(const Ctx &c, int lane, const double *ckpt) {
+RL_HD void bphaseSim(const Ctx &c, int lane) {
   const int32_t *I = c.I, *H = c.H;
   const double *dc = dconst(c);
   double *s = c.s;
@@ -779,7 +786,7 @@ RL_HD void bphaseSim(const Ctx &c, int lane, const double *ckpt) {
   for (int ci = lane; ci < nq; ci += 32) s[H[R_GCMD] + ci] = s[H[R_GQ] + ci] * dc[DC_DT];
   if (lane != 31) return;
   BodyStep b;
-  bodyForward(dc, ckpt + 2 * nq, b);
+  bodyForward(dc, s + H[R_BODY0], b);
   const double dt = dc[DC_DT];
   double *gb = s + H[R_GBODY];
   const V3 g_lm_out = ld3(gb + GB_LM), g_am3 = ld3(gb + GB_AM);
@@ -840,6 +847,7 @@ RL_HD void bphaseInit(const Ctx &c, int lane) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
   for (int e = lane; e < H[H_NQ]; e += 32) s[H[R_GQ] + e] = 0.0, s[H[R_GCMD] + e] = 0.0;
+  if (lane == 0) s[H[R_GQ] + H[H_NQ]] = 0.0;
   for (int e = lane; e < GB_COUNT; e += 32) s[H[R_GBODY] + e] = 0.0;
   for (int e = lane; e < H[H_NTRACK] * 6; e += 32) s[H[R_GPREV] + e] = 0.0;
   for (int e = lane; e < 6; e += 32) s[H[R_GFIRST] + e] = 0.0;

@@ -6,7 +6,7 @@
 // Every frame records the same operator sequence; only the carried values differ.  The product's objective
 // assembly therefore emits, next to the flat tapes of trx_dexsyn_build, this compact description:
 //
-//   * the kinematic tree as a joint table in level order (robot/robotmodel.h:128-148 walks it per frame),
+//   * the kinematic tree as a joint table cut into serial segments (robot/robotmodel.h:128-148 walks it per frame),
 //   * the end effectors with their contact shapes (dexlearn.h:159-217,235-391),
 //   * the dynamic body and the integrator constants (dexopt/src/physics5.h:78-101,174-193,334-371),
 //   * the policy layer shapes (dexopt/src/neural.h:141-190) and the environment weights
@@ -33,7 +33,8 @@ namespace rollout {
 enum {
   H_NJ = 0,       // joints in the pruned pose table (level order; statics first)
   H_NSTATIC,      // leading joints whose pose is a constant
-  H_NLEVELS,      // levels of the non-static part
+  H_NSUPER,       // super-levels of the segment tree
+  H_NSEG,         // segments
   H_NQ,           // controlled (revolute) joints
   H_NEE,          // end effectors
   H_NTRACK,       // links whose previous-frame pose is carried (end-effector links + object)
@@ -50,7 +51,8 @@ enum {
   H_CKPT,         // doubles per frame checkpoint
   H_REGION,       // doubles of per-rollout working storage
   // offsets of integer tables
-  H_I_LEVEL,      // [n_levels + 1] first joint of each level (absolute pose-table index)
+  H_I_SUPER,      // [n_super + 1] first segment of each super-level
+  H_I_SEG,        // [n_seg * 2] {first joint (pose-table index), joints}
   H_I_JOINT,      // [nj * JI_STRIDE]
   H_I_CTRL,       // [nq * CI_STRIDE]
   H_I_EE,         // [n_ee * EI_STRIDE]
@@ -66,7 +68,7 @@ enum {
   H_D_STATIC,     // [n_static * 7] constant poses
   // offsets inside the per-rollout region (doubles)
   R_POSE, R_PREV, R_LQ, R_GPOSE, R_GC, R_Q, R_CMD, R_VEL, R_GQ, R_GCMD, R_BODY, R_GBODY, R_CG, R_GCG, R_FIRST,
-  R_GFIRST, R_GPREV, R_EE, R_GOBJ, R_GPREVOBJ, R_BODYTMP,
+  R_GFIRST, R_GPREV, R_EE, R_GOBJ, R_GPREVOBJ, R_BODY0,
   H_COUNT
 };
 
@@ -82,7 +84,7 @@ enum { EI_LINK = 0, EI_KIND, EI_NPLANES, EI_PLANE0, EI_NROWS, EI_TRACK, EI_ROW, 
 enum { ED_CENTER = 0, ED_RADIUS = 3, ED_LENGTH, ED_STRIDE };
 // per-end-effector scratch in the region
 enum { EE_C1 = 0, EE_C2 = 3, EE_V1 = 6, EE_V2 = 9, EE_GC1 = 12, EE_GC2 = 15, EE_GV1 = 18, EE_GV2 = 21, EE_GP = 24,
-       EE_STRIDE = 30 };
+       EE_IMP = 30 /*impulse (3), angular impulse (3) of the frame's contact force*/, EE_STRIDE = 36 };
 // constants
 enum {
   DC_DT = 0, DC_INV_DT, DC_GRAV = 2 /*3: gravity * (mass * dt)*/, DC_DAMP_LIN = 5, DC_DAMP_ANG, DC_INV_MASS,
@@ -136,7 +138,6 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   }
   // static = pose is a constant: fixed joints below fixed joints, hanging off the world
   std::vector<char> is_static(n_all, 0);
-  std::vector<int> depth(n_all, 0);
   for (int j = 0; j < n_all; j++) {
     const auto &jt = m.joints[j];
     if (jt.parent >= j) {
@@ -145,25 +146,66 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     }
     bool parent_static = jt.parent < 0 || is_static[jt.parent];
     is_static[j] = (jt.type == dexsyn::JOINT_FIXED && parent_static) ? 1 : 0;
-    depth[j] = is_static[j] ? 0 : (jt.parent < 0 || is_static[jt.parent] ? 1 : depth[jt.parent] + 1);
   }
-  int n_levels = 0;
-  for (int j = 0; j < n_all; j++)
-    if (need[j]) n_levels = std::max(n_levels, depth[j]);
-  // pose table order: statics, then level 1, 2, ...
-  std::vector<int> order, index(n_all, -1);
-  std::vector<int> level_first;
-  for (int lv = 0; lv <= n_levels; lv++) {
-    level_first.push_back((int)order.size());
-    for (int j = 0; j < n_all; j++)
-      if (need[j] && depth[j] == lv) {
-        index[j] = (int)order.size();
-        order.push_back(j);
+  // The moving part of the tree is cut into *segments*: maximal runs of joints in which every joint is the
+  // only needed child of its predecessor.  One lane walks a segment from its first joint to its last with the
+  // running pose in registers (no shared-memory round trip or warp barrier between the joints of a run);
+  // segments that hang off a joint of another segment form the next *super-level*.
+  std::vector<std::vector<int>> kids(n_all);
+  std::vector<int> roots;
+  for (int j = 0; j < n_all; j++) {
+    if (!need[j] || is_static[j] || m.joints[j].type == dexsyn::JOINT_FLOATING) continue;
+    int par = m.joints[j].parent;
+    if (par >= 0 && !is_static[par]) {
+      if (m.joints[par].type == dexsyn::JOINT_FLOATING) {
+        p.error = "links hanging off the floating joint";
+        return p;
       }
+      kids[par].push_back(j);
+    } else {
+      roots.push_back(j);
+    }
   }
-  level_first.push_back((int)order.size());
+  struct Seg {
+    std::vector<int> joints;
+    int super;
+  };
+  std::vector<Seg> segs;
+  {
+    std::vector<std::pair<int, int>> todo;  // (first joint, super-level)
+    for (int r : roots) todo.push_back({r, 1});
+    for (size_t t = 0; t < todo.size(); t++) {
+      Seg sg;
+      sg.super = todo[t].second;
+      int j = todo[t].first;
+      for (;;) {
+        sg.joints.push_back(j);
+        if (kids[j].size() == 1) {
+          j = kids[j][0];
+          continue;
+        }
+        for (int c : kids[j]) todo.push_back({c, sg.super + 1});
+        break;
+      }
+      segs.push_back(sg);
+    }
+    std::stable_sort(segs.begin(), segs.end(), [](const Seg &x, const Seg &y) { return x.super < y.super; });
+  }
+  const int n_super = segs.empty() ? 0 : segs.back().super;
+  // pose table order: statics, floating joints, then the segments (each contiguous)
+  std::vector<int> order, index(n_all, -1);
+  auto place = [&](int j) {
+    index[j] = (int)order.size();
+    order.push_back(j);
+  };
+  for (int j = 0; j < n_all; j++)
+    if (need[j] && is_static[j]) place(j);
+  const int n_static = (int)order.size();
+  for (int j = 0; j < n_all; j++)
+    if (need[j] && !is_static[j] && m.joints[j].type == dexsyn::JOINT_FLOATING) place(j);
+  for (auto &sg : segs)
+    for (int j : sg.joints) place(j);
   const int nj = (int)order.size();
-  const int n_static = level_first[1];
   const int nq = (int)m.controlled.size();
   const int n_ee = has_policy ? (int)m.end_effectors.size() : 0;
   // only controlled joints that the objective can see matter; the policy still outputs all of them
@@ -180,7 +222,8 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   auto &D = p.d;
   I[H_NJ] = nj;
   I[H_NSTATIC] = n_static;
-  I[H_NLEVELS] = n_levels;
+  I[H_NSUPER] = n_super;
+  I[H_NSEG] = (int)segs.size();
   I[H_NQ] = nq;
   I[H_NEE] = n_ee;
   I[H_OBJ] = index[m.object_joint];
@@ -214,8 +257,16 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   I[H_NSCALAR] = I[H_NX];
 
   // ---- integer tables
-  I[H_I_LEVEL] = (int)I.size();
-  for (int lv = 1; lv <= n_levels + 1; lv++) I.push_back(level_first[lv]);
+  I[H_I_SUPER] = (int)I.size();
+  for (int sl = 1, sg = 0; sl <= n_super + 1; sl++) {
+    while (sg < (int)segs.size() && segs[sg].super < sl) sg++;
+    I.push_back(sg);
+  }
+  I[H_I_SEG] = (int)I.size();
+  for (auto &sg : segs) {
+    I.push_back(index[sg.joints.front()]);
+    I.push_back((int)sg.joints.size());
+  }
   // tracked links: end-effector links, then the object
   std::vector<int> track;
   auto trackOf = [&](int pose_index) {
@@ -229,11 +280,12 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   const int obj_track = has_policy ? trackOf(index[m.object_joint]) : 0;
   const int n_track = (int)track.size();
   I[H_NTRACK] = n_track;
-  // children lists
+  // branch children of a joint: first joints of other segments that hang off it (the joint that continues
+  // its own segment is simply the next pose-table entry)
   std::vector<std::vector<int>> children(nj);
-  for (int k = 0; k < nj; k++) {
-    int par = m.joints[order[k]].parent;
-    if (par >= 0 && !is_static[par]) children[index[par]].push_back(k);
+  for (auto &sg : segs) {
+    int par = m.joints[sg.joints.front()].parent;
+    if (par >= 0 && !is_static[par]) children[index[par]].push_back(index[sg.joints.front()]);
   }
   I[H_I_JOINT] = (int)I.size();
   I.resize(I.size() + (size_t)nj * JI_STRIDE, 0);
@@ -243,7 +295,7 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     int *ji = &I[I[H_I_JOINT] + k * JI_STRIDE];
     ji[JI_PARENT] = jt.parent >= 0 ? index[jt.parent] : -1;
     ji[JI_TYPE] = jt.type;
-    ji[JI_CTRL] = jt.control;
+    ji[JI_CTRL] = jt.type == dexsyn::JOINT_REVOLUTE ? jt.control : nq;  // n_q: a slot nobody reads
     ji[JI_CHILD0] = (int)child_lists.size();
     ji[JI_NCHILD] = (int)children[k].size();
     ji[JI_TRACK] = -1;
@@ -277,6 +329,7 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     for (int c = 0; c < 3; c++) jd[JD_AXIS + c] = jt.axis[c];
     Q4 r{jt.origin[3], jt.origin[4], jt.origin[5], jt.origin[6]};
     V3 ca = qrot(r, V3{jt.axis[0], jt.axis[1], jt.axis[2]});
+    if (jt.type != dexsyn::JOINT_REVOLUTE) ca = V3{0, 0, 0};
     jd[JD_CAXIS + 0] = ca.x;
     jd[JD_CAXIS + 1] = ca.y;
     jd[JD_CAXIS + 2] = ca.z;
@@ -405,17 +458,18 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     I[key] = off;
     off += n;
   };
-  take(R_POSE, nj * 7);
+  // carried state first, in checkpoint order: a checkpoint is one contiguous copy of it
+  take(R_Q, nq);
+  take(R_CMD, nq);
+  take(R_BODY, B_COUNT);
   take(R_PREV, n_track * 7);
+  take(R_POSE, nj * 7);
   take(R_LQ, nj * 4);
   take(R_GPOSE, nj * 6);
   take(R_GC, nj * 6);
-  take(R_Q, nq);
-  take(R_CMD, nq);
   take(R_VEL, std::max(nq, 1));
-  take(R_GQ, nq);
+  take(R_GQ, nq + 1);
   take(R_GCMD, nq);
-  take(R_BODY, B_COUNT);
   take(R_GBODY, GB_COUNT);
   take(R_CG, 3);
   take(R_GCG, 3);
@@ -425,7 +479,7 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   take(R_EE, n_ee * EE_STRIDE);
   take(R_GOBJ, n_ee * 6);
   take(R_GPREVOBJ, n_ee * 6);
-  take(R_BODYTMP, 16);
+  take(R_BODY0, B_COUNT);
   I[H_REGION] = padTo(off, 2);
   // checkpoint: joint positions, commands, body state, tracked previous poses
   I[H_CKPT] = nq + nq + B_COUNT + n_track * 7;

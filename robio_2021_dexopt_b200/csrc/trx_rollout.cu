@@ -65,46 +65,67 @@ struct KArgs {
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): g = lane >> 2, t = lane & 3;
 // A (8x4, row) a = A[g][t], B (4x8, col) b = B[t][g], C (8x8) c0, c1 = C[g][2t], C[g][2t+1]
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
 
-// Y[g][n] = sum_k X[g][k] W[k][n] + bias[n]   for the 8 rollout rows g; output tiles of 8 columns over the warps
-__device__ __forceinline__ void denseForward(const double *X, int sX, const double *W, int sW, const double *bias,
-                                             double *Y, int sY, int k_pad, int n_out, int warp, int n_warps, int lane) {
+// C[g][n] = sum_k X[g][k] B[k][n] for the 8 rollout rows g, n < n_cols: output tiles of 8 columns dealt over the
+// warps, two tiles per trip and two accumulator chains per tile so that four DMMAs are in flight (a dependent
+// DMMA issues every ~26 cycles, scripts/microbench/fp64_peak.cu).  B[k][n] = W[k * wk + n * wn]: the forward
+// products read the weights as stored (wk = row stride, wn = 1), the input adjoints read them transposed.
+// epi(g, n, value) receives every element of the tile.
+template <class Epi>
+__device__ __forceinline__ void denseTiles(const double *X, int sX, const double *W, int wk, int wn, int k_pad, int n_cols,
+                                           int warp, int n_warps, int lane, Epi epi) {
   const int g = lane >> 2, t = lane & 3;
-  for (int n0 = warp * 8; n0 < n_out; n0 += n_warps * 8) {
-    double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
-    const double *xa = X + g * sX + t, *wb = W + t * sW + n0 + g;
+  const double *xa = X + g * sX + t;
+  for (int n0 = warp * 8; n0 < n_cols; n0 += 2 * n_warps * 8) {
+    const int n1 = n0 + n_warps * 8;
+    const bool two = n1 < n_cols;
+    const double *wa = W + t * wk + (n0 + g) * wn, *wb = W + t * wk + (n1 + g) * wn;
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
     int k = 0;
-    for (; k + 8 <= k_pad; k += 8) {
-      dmma884(c0, c1, xa[k], wb[k * sW]);
-      dmma884(d0, d1, xa[k + 4], wb[(k + 4) * sW]);
+    if (two) {
+      for (; k + 8 <= k_pad; k += 8) {
+        const double x0 = xa[k], x1 = xa[k + 4];
+        dmma884(a0, a1, x0, wa[k * wk]);
+        dmma884(c0, c1, x0, wb[k * wk]);
+        dmma884(b0, b1, x1, wa[(k + 4) * wk]);
+        dmma884(d0, d1, x1, wb[(k + 4) * wk]);
+      }
+      if (k < k_pad) {
+        const double x0 = xa[k];
+        dmma884(a0, a1, x0, wa[k * wk]);
+        dmma884(c0, c1, x0, wb[k * wk]);
+      }
+      epi(g, n1 + 2 * t, c0 + d0);
+      epi(g, n1 + 2 * t + 1, c1 + d1);
+    } else {
+      for (; k + 8 <= k_pad; k += 8) {
+        dmma884(a0, a1, xa[k], wa[k * wk]);
+        dmma884(b0, b1, xa[k + 4], wa[(k + 4) * wk]);
+      }
+      if (k < k_pad) dmma884(a0, a1, xa[k], wa[k * wk]);
     }
-    if (k < k_pad) dmma884(c0, c1, xa[k], wb[k * sW]);
-    Y[g * sY + n0 + 2 * t] = (c0 + d0) + bias[n0 + 2 * t];
-    Y[g * sY + n0 + 2 * t + 1] = (c1 + d1) + bias[n0 + 2 * t + 1];
+    epi(g, n0 + 2 * t, a0 + b0);
+    epi(g, n0 + 2 * t + 1, a1 + b1);
   }
 }
 
-// GX[g][i] = sum_j GY[g][j] W[i][j]
-__device__ __forceinline__ void denseBackwardX(const double *GY, int sY, const double *W, int sW, double *GX, int sX,
-                                               int k_pad, int n_in, int warp, int n_warps, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  for (int i0 = warp * 8; i0 < n_in; i0 += n_warps * 8) {
-    double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
-    const double *ya = GY + g * sY + t, *wb = W + (i0 + g) * sW + t;
-    int k = 0;
-    for (; k + 8 <= k_pad; k += 8) {
-      dmma884(c0, c1, ya[k], wb[k]);
-      dmma884(d0, d1, ya[k + 4], wb[k + 4]);
-    }
-    if (k < k_pad) dmma884(c0, c1, ya[k], wb[k]);
-    GX[g * sX + i0 + 2 * t] = c0 + d0;
-    GX[g * sX + i0 + 2 * t + 1] = c1 + d1;
+// development aid: -DTRX_ROLLOUT_PROFILE accumulates clock64() per phase (thread 0 of every CTA, CTA 0 reported)
+#ifdef TRX_ROLLOUT_PROFILE
+#define PH(idx, ...)                                  \
+  {                                                   \
+    long long _t0 = clock64();                        \
+    __VA_ARGS__;                                      \
+    if (tid == 0) sprof[idx] += clock64() - _t0;      \
   }
-}
+__device__ long long g_rollout_prof[64];
+#else
+#define PH(idx, ...) \
+  { __VA_ARGS__; }
+#endif
 
 template <int NW, int MAXT>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -112,7 +133,11 @@ __global__ void __launch_bounds__(NW * 32, 1)
   extern __shared__ double sm[];
   const int32_t *H = hdr.v;
   const int tid = threadIdx.x, nt = NW * 32, warp = tid >> 5, lane = tid & 31;
-  const int n_in = H[H_NIN], n_hid = H[H_NHID], n_out = H[H_NOUT], n_layers = H[H_NLAYERS], L = H[H_NLEVELS];
+#ifdef TRX_ROLLOUT_PROFILE
+  __shared__ long long sprof[64];
+  if (tid < 64) sprof[tid] = 0;
+#endif
+  const int n_in = H[H_NIN], n_hid = H[H_NHID], n_out = H[H_NOUT], n_layers = H[H_NLAYERS], L = H[H_NSUPER];
   const int n1 = n_layers == 2 ? n_hid : n_out;  // output width of the first layer
 
   // ---- stage the plan and the weights
@@ -159,9 +184,6 @@ __global__ void __launch_bounds__(NW * 32, 1)
   double *XS = sm + a.o_X, *HS = sm + a.o_H, *AS = sm + a.o_A, *OS = sm + a.o_O;
   double *GXS = sm + a.o_GX, *GHS = sm + a.o_GH, *GOS = sm + a.o_GO;
   const int k1 = (n_in + 3) & ~3, k2 = (n_hid + 3) & ~3;
-  const int s1x = a.s_X;                                   // row stride of the first layer's input
-  const int s1y = n_layers == 2 ? a.s_H : a.s_O;           // and of its output / output adjoint
-  double *Y1 = n_layers == 2 ? HS : OS, *GY1 = n_layers == 2 ? GHS : GOS;
 
   Ctx c;
   c.H = H;
@@ -180,126 +202,180 @@ __global__ void __launch_bounds__(NW * 32, 1)
   for (int u = 0; u < (MAXT > 0 ? MAXT : 1); u++) acc[u][0] = acc[u][1] = 0.0;
   double gb0 = 0.0, gb1 = 0.0;  // bias gradients: element tid and tid + nt of {b1, b2}
 
-  // the frame's forward phases for this warp's rollout; recompute: values only (adjoint sweep)
-  auto forwardFrame = [&](const Ctx &cc, int f, bool active, double &ls, bool recompute) {
-    if (active) {
-      phaseSim(cc, lane);
-      __syncwarp();
-      for (int lv = 1; lv <= L; lv++) {
-        phaseChain(cc, lane, lv);
-        __syncwarp();
-      }
-      phaseObserve(cc, lane, f, ls);
-    }
-    if (!n_layers) return;
-    __syncthreads();
-    denseForward(XS, s1x, sW1, a.s_W1, sB1, Y1, s1y, k1, n1, warp, NW, lane);
-    __syncthreads();
-    if (n_layers == 2) {
-      if (active) phaseHidden(cc, lane, f, ls);
-      __syncthreads();
-      denseForward(AS, a.s_H, sW2, a.s_W2, sB2, OS, a.s_O, k2, n_out, warp, NW, lane);
-      __syncthreads();
-    }
-    if (active) {
-      phaseControl(cc, lane, f, ls);
-      __syncwarp();
-      phaseContact1(cc, lane, f, ls);
-      __syncwarp();
-      phaseContact2(cc, lane, f);
-      __syncwarp();
-      if (!recompute) {
-        phaseContact3(cc, lane, f, ls);
-        __syncwarp();
-        phaseContactSum(cc, lane);
-        __syncwarp();
-      }
-    }
-  };
+  const double w_reg = sD[H[H_D_CONST] + DC_W_REG], w_creg = sD[H[H_D_CONST] + DC_W_CREG];
+  const int nq = H[H_NQ], rows_frame = H[H_ROWS_FRAME];
+  const int gi = lane >> 2, t4 = lane & 3;
+  constexpr int kPre = 6;  // checkpoint doubles per lane (H_CKPT <= 192, checked by the host)
+  double pre[kPre];
 
   for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
-    const long local = (long)grp * NW + warp;  // rollout inside this launch
-    const bool active = local < a.count;
+    const long grp_first = (long)grp * NW;  // first rollout of the group inside this launch
+    const int live = (int)min((long)NW, a.count - grp_first);  // rows of the group that are rollouts
+    const long local = grp_first + warp;
+    const bool active = warp < live;
     const long rollout = a.first + local;
     double *ckpt = a.ckpt + (size_t)local * T * CK;
+    // element (row, g) of the group's residual rows / seeds at [row * R + g]
+    double *grp_r = a.r_out ? a.r_out + H[H_NSCALAR] + a.first + grp_first : nullptr;
+    const double *grp_seed = a.seed ? a.seed + H[H_NSCALAR] + a.first + grp_first : nullptr;
     c.r_out = (a.r_out && active) ? a.r_out + H[H_NSCALAR] + rollout : nullptr;
     c.seed = nullptr;
+    c.emit = true;
     if (!active) {
       // an idle warp of the last group: its rows of the activation matrices must stay zero
       for (int e = lane; e < a.s_X; e += 32) c.x[e] = 0.0, c.gx[e] = 0.0;
       for (int e = lane; e < a.s_H; e += 32) c.h[e] = 0.0, c.a[e] = 0.0, c.gh[e] = 0.0;
       for (int e = lane; e < a.s_O; e += 32) c.out[e] = 0.0, c.gout[e] = 0.0;
     }
-    // ---- forward sweep
     if (active) {
       const double pr[3] = {a.params[rollout], a.params[a.R + rollout], a.params[2 * a.R + rollout]};
       phaseInit(c, lane, pr);
       __syncwarp();
-      for (int lv = 1; lv <= L; lv++) {
-        phaseChain(c, lane, lv);
+      for (int sl = 1; sl <= L; sl++) {
+        phaseChain(c, lane, sl);
         __syncwarp();
       }
     }
-    for (int f = 0; f < T; f++) {
-      if (active) {
-        phaseBeginFrame(c, lane, ckpt + (size_t)f * CK);
-        __syncwarp();
+    // One loop over both sweeps so that the frame's forward code exists once: steps 0 .. T-1 are the forward
+    // sweep (frame = step), steps T .. 2T-1 the adjoint sweep (frame = 2T-1-step: recompute it from its
+    // checkpoint, then its adjoint).
+    const int n_steps = a.want_grad ? 2 * T : T;
+    for (int step = 0; step <= n_steps; step++) {
+      const bool rec = step >= T;
+      const int f = rec ? 2 * T - 1 - step : step;
+      if (step == T) {
+        // between the sweeps: terminal goals, then the adjoint's carried state
+        if (active) {
+          phaseTerminal(c, lane, loss);
+          __syncwarp();
+        }
+        if (!a.want_grad) break;
+        c.r_out = nullptr;
+        c.emit = false;
+        c.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
+        if (active) {
+          bphaseInit(c, lane);
+          const double *ck = ckpt + (size_t)(T - 1) * CK;
+#pragma unroll
+          for (int i = 0; i < kPre; i++) pre[i] = (lane + 32 * i < CK) ? ck[lane + 32 * i] : 0.0;
+          __syncwarp();
+        }
       }
-      forwardFrame(c, f, active, loss, false);
-    }
-    if (active) {
-      phaseTerminal(c, lane, loss);
-      __syncwarp();
-    }
-    if (!a.want_grad) continue;
+      if (step == n_steps) break;
 
-    // ---- adjoint sweep
-    Ctx cb = c;
-    cb.r_out = nullptr;
-    cb.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
-    double unused = 0.0;
-    if (active) {
-      bphaseInit(cb, lane);
-      __syncwarp();
-    }
-    for (int f = T - 1; f >= 0; f--) {
-      const double *ck = ckpt + (size_t)f * CK;
+      // ---- the frame, forward
       if (active) {
-        phaseLoadCheckpoint(cb, lane, ck);
-        __syncwarp();
+        if (!rec) {
+          PH(12, phaseBeginFrame(c, lane, f, ckpt + (size_t)f * CK); __syncwarp());
+        } else {
+          PH(13, phaseLoadCheckpoint(c, lane, pre); __syncwarp());
+          if (f > 0) {  // the next checkpoint lands while this frame is being worked on
+            const double *ck = ckpt + (size_t)(f - 1) * CK;
+#pragma unroll
+            for (int i = 0; i < kPre; i++) pre[i] = (lane + 32 * i < CK) ? ck[lane + 32 * i] : 0.0;
+          }
+        }
+        PH(0, phaseSim(c, lane); __syncwarp());
+        PH(1, for (int sl = 1; sl <= L; sl++) {
+          phaseChain(c, lane, sl);
+          __syncwarp();
+        });
+        PH(2, phaseObserve(c, lane, f, loss));
       }
-      forwardFrame(cb, f, active, unused, true);
+      if (n_layers) {
+        // The policy layers' epilogues carry what follows them: activity / command regularisation rows and
+        // tanh (dexenv_grasp.h:137-146,186-199), so the hidden and control steps cost no phase of their own.
+        const long row_act = (long)f * rows_frame + H[H_ROW_ACT], row_cmd = (long)f * rows_frame + H[H_ROW_CMD];
+        PH(3, __syncthreads());
+        if (n_layers == 2) {
+          PH(4, denseTiles(XS, a.s_X, sW1, a.s_W1, 1, k1, n_hid, warp, NW, lane, [=, &loss](int g, int j, double v) {
+            v += sB1[j];
+            HS[g * a.s_H + j] = v;
+            AS[g * a.s_H + j] = tanh(v);
+            if (!rec && j < n_hid && g < live) {
+              const double r = v * w_reg;
+              loss += r * r;
+              if (grp_r) grp_r[(row_act + j) * a.R + g] = r;
+            }
+          }));
+          PH(3, __syncthreads());
+        }
+        {
+          const double *Xl = n_layers == 2 ? AS : XS, *Wl = n_layers == 2 ? sW2 : sW1, *Bl = n_layers == 2 ? sB2 : sB1;
+          const int sXl = n_layers == 2 ? a.s_H : a.s_X, sWl = n_layers == 2 ? a.s_W2 : a.s_W1;
+          double *vel = sm + a.o_region + H[R_VEL];
+          const int region = H[H_REGION];
+          PH(6, denseTiles(Xl, sXl, Wl, sWl, 1, n_layers == 2 ? k2 : k1, n_out, warp, NW, lane,
+                           [=, &loss](int g, int j, double v) {
+                             v += Bl[j];
+                             OS[g * a.s_O + j] = v;
+                             if (j < nq && g < NW) vel[g * region + j] = tanh(v);
+                             if (!rec && j < n_out && g < live) {
+                               const double r = v * w_creg;
+                               loss += r * r;
+                               if (grp_r) grp_r[(row_cmd + j) * a.R + g] = r;
+                             }
+                           }));
+        }
+        PH(3, __syncthreads());
+        if (active) {
+          PH(8, phaseContact1(c, lane, f, loss); __syncwarp());
+          PH(9, phaseContact2(c, lane, f); __syncwarp());
+          if (!rec) {
+            PH(10, phaseContact3(c, lane, f, loss); __syncwarp());
+          }
+        }
+      }
+      if (!rec) continue;
+
+      // ---- the frame, adjoint
       if (active) {
-        bphaseBegin(cb, lane, f);
-        __syncwarp();
-        bphaseBegin2(cb, lane, f);
-        __syncwarp();
+        PH(32, bphaseBegin(c, lane, f); __syncwarp(); if (f == T - 1 || f == 0) {
+          bphaseBegin2(c, lane, f);
+          __syncwarp();
+        });
         if (n_layers) {
-          bphaseContact3(cb, lane, f);
-          __syncwarp();
-          bphaseContact2(cb, lane, f);
-          __syncwarp();
-          bphaseContact1(cb, lane, f);
-          __syncwarp();
-          bphaseControl(cb, lane, f);
+          PH(33, bphaseContact3(c, lane, f); __syncwarp());
+          PH(34, bphaseContact2(c, lane, f); __syncwarp());
+          PH(35, bphaseContact1(c, lane, f); __syncwarp());
+          PH(36, bphaseControl(c, lane, f));
         }
       }
       if (n_layers) {
-        __syncthreads();
-        // adjoint of the last layer: input adjoint, then dW (register tiles) and db
-        if (n_layers == 2) denseBackwardX(GOS, a.s_O, sW2, a.s_W2, GHS, a.s_H, (n_out + 3) & ~3, n_hid, warp, NW, lane);
-        else denseBackwardX(GOS, a.s_O, sW1, a.s_W1, GXS, a.s_X, (n_out + 3) & ~3, n_in, warp, NW, lane);
+        PH(37, __syncthreads());
+        // adjoint of the last layer: input adjoint (with the tanh / activity-row adjoint of the hidden layer in
+        // its epilogue), then dW (register tiles) and db
+        if (n_layers == 2) {
+          const long row_act = (long)f * rows_frame + H[H_ROW_ACT];
+          PH(38, denseTiles(GOS, a.s_O, sW2, 1, a.s_W2, (n_out + 3) & ~3, n_hid, warp, NW, lane,
+                            [=](int g, int i, double v) {
+                              const bool on = g < live && i < n_hid;
+                              const double av = AS[g * a.s_H + i];
+                              const double sd = grp_seed ? (on ? grp_seed[(row_act + i) * a.R + g] : 0.0)
+                                                         : HS[g * a.s_H + i] * w_reg;
+                              GHS[g * a.s_H + i] = on ? v * (1.0 - av * av) + sd * w_reg : 0.0;
+                            }));
+        } else {
+          PH(38, denseTiles(GOS, a.s_O, sW1, 1, a.s_W1, (n_out + 3) & ~3, n_in, warp, NW, lane,
+                            [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
+        }
+#ifdef TRX_ROLLOUT_PROFILE
+        long long _tw = clock64();
+#endif
         if (MAXT > 0) {
-          const int gi = lane >> 2, t4 = lane & 3;
+          // dW += X^T GY, K = the 8 rollouts = two DMMAs per 8x8 tile; the first DMMA of every tile, then the second,
+          // so that consecutive DMMAs never wait on each other's accumulator.  With two layers the first
+          // layer's tiles wait for its output adjoint (below).
+          const int sx = n_layers == 2 ? a.s_H : a.s_X;
 #pragma unroll
-          for (int u = 0; u < MAXT; u++) {
-            const int tl = warp + u * NW;
-            // with two layers the first layer's tiles wait for its output adjoint (below)
-            if (tl < a.n_tiles && (n_layers == 1 || tl >= a.tiles_1)) {
-              const int sx = tl < a.tiles_1 ? a.s_X : a.s_H, sy = a.s_O;
-              const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
-              dmma884(acc[u][0], acc[u][1], xa[t4 * sx], yb[t4 * sy]);
-              dmma884(acc[u][0], acc[u][1], xa[(t4 + 4) * sx], yb[(t4 + 4) * sy]);
+          for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int u = 0; u < MAXT; u++) {
+              const int tl = warp + u * NW;
+              if (tl < a.n_tiles && (n_layers == 1 || tl >= a.tiles_1)) {
+                const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
+                dmma884(acc[u][0], acc[u][1], xa[(t4 + 4 * half) * sx], yb[(t4 + 4 * half) * a.s_O]);
+              }
             }
           }
         }
@@ -315,20 +391,26 @@ __global__ void __launch_bounds__(NW * 32, 1)
             else gb1 += sgy;
           }
         }
-        __syncthreads();
+#ifdef TRX_ROLLOUT_PROFILE
+        if (tid == 0) sprof[39] += clock64() - _tw;
+#endif
+        PH(37, __syncthreads());
         if (n_layers == 2) {
-          if (active) bphaseHidden(cb, lane, f);
-          __syncthreads();
-          denseBackwardX(GHS, a.s_H, sW1, a.s_W1, GXS, a.s_X, k2, n_in, warp, NW, lane);
+          PH(41, denseTiles(GHS, a.s_H, sW1, 1, a.s_W1, k2, n_in, warp, NW, lane,
+                            [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
+#ifdef TRX_ROLLOUT_PROFILE
+          _tw = clock64();
+#endif
           if (MAXT > 0) {
-            const int gi = lane >> 2, t4 = lane & 3;
 #pragma unroll
-            for (int u = 0; u < MAXT; u++) {
-              const int tl = warp + u * NW;
-              if (tl < a.tiles_1) {
-                const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
-                dmma884(acc[u][0], acc[u][1], xa[t4 * a.s_X], yb[t4 * a.s_H]);
-                dmma884(acc[u][0], acc[u][1], xa[(t4 + 4) * a.s_X], yb[(t4 + 4) * a.s_H]);
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+              for (int u = 0; u < MAXT; u++) {
+                const int tl = warp + u * NW;
+                if (tl < a.tiles_1) {
+                  const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
+                  dmma884(acc[u][0], acc[u][1], xa[(t4 + 4 * half) * a.s_X], yb[(t4 + 4 * half) * a.s_H]);
+                }
               }
             }
           }
@@ -339,22 +421,27 @@ __global__ void __launch_bounds__(NW * 32, 1)
             if (slot == 0) gb0 += sgy;
             else gb1 += sgy;
           }
-          __syncthreads();
+#ifdef TRX_ROLLOUT_PROFILE
+          if (tid == 0) sprof[42] += clock64() - _tw;
+#endif
+          PH(37, __syncthreads());
         }
       }
       if (active) {
-        bphaseObserve(cb, lane, f);
-        __syncwarp();
-        for (int lv = L; lv >= 1; lv--) {
-          bphaseChain(cb, lane, lv);
+        PH(43, bphaseObserve(c, lane, f); __syncwarp());
+        PH(44, for (int sl = L; sl >= 1; sl--) {
+          bphaseChain(c, lane, sl);
           __syncwarp();
-        }
-        bphaseSim(cb, lane, ck);
-        __syncwarp();
+        });
+        PH(45, bphaseSim(c, lane); __syncwarp());
       }
     }
   }
 
+#ifdef TRX_ROLLOUT_PROFILE
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < 64) g_rollout_prof[tid] = sprof[tid];
+#endif
   // ---- this CTA's partial loss and gradient
   double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
   {
@@ -500,6 +587,10 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
     return TRX_ERR_INVALID;
   }
   const auto &I = ro->plan.i;
+  if (I[H_CKPT] > 192) {
+    err = "re-rolled objective: carried state exceeds the checkpoint prefetch registers (192 doubles)";
+    return TRX_ERR_UNSUPPORTED;
+  }
   if (I[H_NLAYERS] == 0 || I[H_NX] == 0) {
     err = "re-rolled objective: no policy, nothing to differentiate";
     return TRX_ERR_UNSUPPORTED;
@@ -631,7 +722,7 @@ uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key) {
   if (k == "shared_bytes") return ro->smem_bytes;
   if (k == "tiles_per_warp") return ro->maxt;
   if (k == "n_joints") return I[H_NJ];
-  if (k == "n_levels") return I[H_NLEVELS];
+  if (k == "n_levels") return I[H_NSUPER];
   if (k == "n_controlled") return I[H_NQ];
   if (k == "n_end_effectors") return I[H_NEE];
   if (k == "n_in") return I[H_NIN];
@@ -685,3 +776,24 @@ trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out,
 }
 
 uint64_t trxRolloutLaunches(const trx_rollout *ro) { return ro->launches; }
+
+#ifdef TRX_ROLLOUT_PROFILE
+extern "C" void trx_rollout_profile_dump() {
+  long long h[64];
+  cudaMemcpyFromSymbol(h, g_rollout_prof, sizeof(h));
+  const char *names[64] = {};
+  names[0] = "sim", names[1] = "chain", names[2] = "observe", names[3] = "barriers(fwd)", names[4] = "dense1", names[5] = "hidden";
+  names[6] = "dense2", names[7] = "control", names[8] = "contact1", names[9] = "contact2", names[10] = "contact3";
+  names[11] = "contactsum", names[12] = "beginframe+ckpt", names[13] = "loadckpt";
+  names[32] = "b.begin", names[33] = "b.contact3", names[34] = "b.contact2", names[35] = "b.contact1", names[36] = "b.control";
+  names[37] = "b.barriers", names[38] = "b.dense2 gx", names[39] = "b.dW2+db2", names[40] = "b.hidden", names[41] = "b.dense1 gx";
+  names[42] = "b.dW1+db1", names[43] = "b.observe", names[44] = "b.chain", names[45] = "b.sim";
+  long long total = 0;
+  for (int i = 0; i < 64; i++) total += h[i];
+  for (int i = 0; i < 64; i++) {
+    if (!h[i]) continue;
+    const char *n = i >= 16 && i < 32 ? names[i - 16] : names[i];
+    std::printf("%-2d %s%-18s %12lld cycles %5.1f%%\n", i, i >= 16 && i < 32 ? "re." : "", n ? n : "?", h[i], 100.0 * h[i] / total);
+  }
+}
+#endif

@@ -44,3 +44,9 @@ ms = e0.elapsed_time(e1) / steps
 out = d_out.cpu().numpy()
 print("frames %d lanes %d: %.3f ms per evaluation, %.2f M timestep*rollouts/s, loss %.10g |g| %.6g" %
       (frames, lanes, ms, frames * lanes / ms / 1e3, out[0], np.linalg.norm(out[1:])))
+
+lib = pkg._native.lib()
+if hasattr(lib, "trx_rollout_profile_dump"):
+    import ctypes
+    sys.stdout.flush()
+    lib.trx_rollout_profile_dump()

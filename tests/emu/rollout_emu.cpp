@@ -72,7 +72,7 @@ int rollout_emu_info(const char *options, const char *key, long *value) {
     else if (k == "checkpoint_doubles") *value = I[H_CKPT];
     else if (k == "region_doubles") *value = I[H_REGION];
     else if (k == "n_joints") *value = I[H_NJ];
-    else if (k == "n_levels") *value = I[H_NLEVELS];
+    else if (k == "n_levels") *value = I[H_NSUPER];
     else throw std::runtime_error("unknown key " + k);
     return 0;
   } catch (const std::exception &e) {
@@ -90,7 +90,7 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
     const auto &I = p.plan.i;
     const auto &D = p.plan.d;
     const int T = p.frames, nq = I[H_NQ], n_in = I[H_NIN], n_hid = I[H_NHID], n_out = I[H_NOUT];
-    const int n_layers = I[H_NLAYERS], L = I[H_NLEVELS];
+    const int n_layers = I[H_NLAYERS], L = I[H_NSUPER];
     const long nx = I[H_NX], n_scalar = I[H_NSCALAR];
     const double *W1 = x + I[H_W1], *b1 = x + I[H_B1], *W2 = x + I[H_W2], *b2 = x + I[H_B2];
     const double reg = D[I[H_D_CONST] + DC_W_REG];
@@ -119,6 +119,7 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
       c.seed = nullptr;
       c.r_stride = lanes;
       c.frames = T;
+      c.emit = true;
       double lane_loss[32] = {0};
       double pr[3] = {params[0 * lanes + g0], params[1 * lanes + g0], params[2 * lanes + g0]};
       auto forwardFrame = [&](int f, const Ctx &cc, double *ll, bool store) {
@@ -138,14 +139,13 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
           LANES(phaseContact2(cc, lane, f));
           if (store) {
             LANES(phaseContact3(cc, lane, f, ll[lane]));
-            LANES(phaseContactSum(cc, lane));
           }
         }
       };
       LANES(phaseInit(c, lane, pr));
       for (int lv = 1; lv <= L; lv++) LANES(phaseChain(c, lane, lv));
       for (int f = 0; f < T; f++) {
-        LANES(phaseBeginFrame(c, lane, &ckpt[(size_t)f * I[H_CKPT]]));
+        LANES(phaseBeginFrame(c, lane, f, &ckpt[(size_t)f * I[H_CKPT]]));
         forwardFrame(f, c, lane_loss, true);
       }
       LANES(phaseTerminal(c, lane, lane_loss[lane]));
@@ -154,15 +154,20 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
       // ---- adjoint sweep
       Ctx cb = c;
       cb.r_out = nullptr;
+      cb.emit = false;
       cb.seed = seed_wide ? seed_wide + n_scalar + g0 : nullptr;
       double dummy[32];
       LANES(bphaseInit(cb, lane));
       for (int f = T - 1; f >= 0; f--) {
         const double *ck = &ckpt[(size_t)f * I[H_CKPT]];
-        LANES(phaseLoadCheckpoint(cb, lane, ck));
+        for (int lane = 0; lane < 32; lane++) {
+          double pre[8];
+          for (int i = 0; i < 8; i++) pre[i] = lane + 32 * i < I[H_CKPT] ? ck[lane + 32 * i] : 0.0;
+          phaseLoadCheckpoint(cb, lane, pre);
+        }
         forwardFrame(f, cb, dummy, false);
         LANES(bphaseBegin(cb, lane, f));
-        LANES(bphaseBegin2(cb, lane, f));
+        if (f == T - 1 || f == 0) LANES(bphaseBegin2(cb, lane, f));
         if (n_layers) {
           LANES(bphaseContact3(cb, lane, f));
           LANES(bphaseContact2(cb, lane, f));
@@ -178,7 +183,7 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
         }
         LANES(bphaseObserve(cb, lane, f));
         for (int lv = L; lv >= 1; lv--) LANES(bphaseChain(cb, lane, lv));
-        LANES(bphaseSim(cb, lane, ck));
+        LANES(bphaseSim(cb, lane));
       }
     }
     *loss_out = loss_total;
