@@ -425,11 +425,16 @@ static int cmdBench(const std::map<std::string, std::string> &kv) {
   int threads = (int)getI(kv, "threads", 1);
   double seconds = getD(kv, "seconds", 3.0);
   bool loop = getS(kv, "engine", "simple") == "loop";
+  // Every thread first builds its own runner (own Memory + 6 compiled executables); the clock starts only when
+  // all of them are ready, so the start-up cost is not charged to the rate.  `repeats` windows of `seconds`
+  // each are measured back to back and the median window is reported.
+  int repeats = (int)getI(kv, "repeats", 1);
   std::atomic<long> evals(0);
   std::atomic<bool> stop(false);
+  std::atomic<int> ready(0);
+  std::atomic<bool> go(false);
   std::vector<std::thread> pool;
   std::vector<double> checks(threads, 0.0);
-  auto t0 = std::chrono::steady_clock::now();
   for (int ti = 0; ti < threads; ti++) {
     pool.emplace_back([&, ti]() {
       std::unique_ptr<RefRunner> runp;
@@ -442,7 +447,7 @@ static int cmdBench(const std::map<std::string, std::string> &kv) {
       RefRunner &run = *runp;
       dexsyn::Rng rng(1000 + ti);
       std::vector<double> params(n_param_lane * 8), r, g;
-      while (!stop.load()) {
+      auto evaluate = [&]() {
         for (size_t i = 0; i < params.size(); i++) {
           size_t port = i / 8;
           params[i] = port < 2 ? rng.uniform(-0.01, 0.01) : (port == 2 ? rng.uniform(0, 6.28) : 1.0);
@@ -452,20 +457,44 @@ static int cmdBench(const std::map<std::string, std::string> &kv) {
         run.prepare();       // x_prep
         run.reverse(r, g);   // x_bprop: input, execute, output   (gd.h:50-63)
         checks[ti] += g[0];
+      };
+      evaluate();  // first touch of the memory image is not timed either
+      ready.fetch_add(1);
+      while (!go.load()) std::this_thread::yield();
+      while (!stop.load()) {
+        evaluate();
         evals.fetch_add(1);
       }
     });
   }
-  while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds)
-    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  while (ready.load() < threads) std::this_thread::sleep_for(std::chrono::milliseconds(5));
+  go.store(true);
+  std::vector<double> rates;
+  const double units = 8.0 * frames * getI(kv, "outer", 1);
+  auto t_prev = std::chrono::steady_clock::now();
+  long n_prev = evals.load();
+  double dt_total = 0;
+  for (int rep = 0; rep < repeats; rep++) {
+    std::this_thread::sleep_for(std::chrono::duration<double>(seconds));
+    auto t_now = std::chrono::steady_clock::now();
+    long n_now = evals.load();
+    double dt = std::chrono::duration<double>(t_now - t_prev).count();
+    rates.push_back((double)(n_now - n_prev) * units / dt);
+    dt_total += dt;
+    t_prev = t_now;
+    n_prev = n_now;
+  }
   stop.store(true);
   for (auto &t : pool) t.join();
-  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  long n = evals.load();
-  double rate = (double)n * 8.0 * frames * getI(kv, "outer", 1) / dt;  // timestep*rollouts / s
+  long n = n_prev;
+  std::vector<double> sorted = rates;
+  std::sort(sorted.begin(), sorted.end());
+  double rate = sorted[sorted.size() / 2];
   std::printf("{\"evals\": %ld, \"seconds\": %.4f, \"threads\": %d, \"frames\": %d, \"lanes\": 8, "
-              "\"step_rollouts_per_s\": %.3f, \"engine\": \"%s\"}\n",
-              n, dt, threads, frames, rate, loop ? "loop" : "simple");
+              "\"step_rollouts_per_s\": %.3f, \"engine\": \"%s\", \"windows\": [",
+              n, dt_total, threads, frames, rate, loop ? "loop" : "simple");
+  for (size_t i = 0; i < rates.size(); i++) std::printf("%s%.1f", i ? ", " : "", rates[i]);
+  std::printf("]}\n");
   return 0;
 }
 
