@@ -69,6 +69,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(OBJ_DIR, exist_ok=True)
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-c"]
+    # development builds: TRX_NVCC_EXTRA="-DTRX_ROLLOUT_PROFILE" adds the per-phase clocks of csrc/trx_rollout.cu
+    compile_flags += os.environ.get("TRX_NVCC_EXTRA", "").split()
     if verbose:
         compile_flags = ["-Xptxas", "-v"] + compile_flags
     jobs, objs = [], []

@@ -1,11 +1,14 @@
 // rollout_frame.h -- one frame of dexopt's rollout objective, forward and adjoint, hand-written.
 //
 // What the reference executes per frame as ~1 500 interpreted tape instructions (after dense-layer
-// fusion; ~12 000 before) is written out here as a fixed sequence of *phases*.  One warp owns one
-// rollout; inside a phase every lane works on its own item (a joint, a policy output, one side of
-// a contact) and touches only that item's storage, so the only synchronisation between phases is
-// __syncwarp(); the policy layers are the one place where the rollouts of a CTA meet (DMMA tiles
-// over rollouts, trx_rollout.cu).
+// fusion; ~12 000 before) is written out here as a fixed sequence of *phases*.  Inside a phase every
+// item (a joint, a policy output, one side of a contact) is independent of the others and touches only
+// its own storage, so whoever runs the phase may deal the items of a rollout to lanes in any way
+// (`lane` = first item, stride 32) and only has to synchronise between phases.  The kernel
+// (trx_rollout.cu) puts the same item of the 8 rollouts of a CTA into neighbouring lanes; the forward
+// kinematics and its adjoint are warp scans instead (fkRound*: one warp per rollout, a lane per joint),
+// the body step is one lane per rollout (phaseBody / bphaseBody), and the policy layers are the one
+// place where the rollouts of a CTA meet (DMMA tiles over rollouts, trx_rollout.cu).
 //
 // Forward follows csrc/assembly/dexsyn_assemble.h statement by statement, which in turn restates
 //   simulator step        dexopt/src/physics5.h:106-121,174-193,334-391,572-589
@@ -60,7 +63,6 @@ struct Ctx {
   const double *seed;  // adjoint seeds by residual row (null: the residuals themselves, g = J^T r)
   long r_stride;
   int frames;
-  bool emit;         // false: values only (the adjoint sweep recomputes a frame without counting it again)
 };
 
 // ---- small load/store helpers
@@ -80,7 +82,6 @@ RL_HD const double *dconst(const Ctx &c) { return c.D + c.H[H_D_CONST]; }
 
 // residual row: value into the loss (and the residual vector when asked for)
 RL_HD void emit(const Ctx &c, long row, double v, double &loss) {
-  if (!c.emit) return;
   loss += v * v;
   if (c.r_out) c.r_out[row * c.r_stride] = v;
 }
@@ -186,8 +187,8 @@ RL_HD void bodyForward(const double *dc, const double *body, BodyStep &b) {
   b.Dp = trxvm::pmul(b.C, PoseV{{0, 0, 0}, b.Bp.r});
 }
 
-// simulator step: lane 31 integrates the body and poses the object link, lanes < n_q run the velocity
-// controllers (physics5.h:373-391) and form the local joint rotations origin.r * R(axis, q)
+// simulator step, joints: the velocity controllers (physics5.h:373-391) and the local joint rotations
+// origin.r * R(axis, q)
 RL_HD void phaseSim(const Ctx &c, int lane) {
   const int32_t *I = c.I, *H = c.H;
   const double *dc = dconst(c);
@@ -200,7 +201,13 @@ RL_HD void phaseSim(const Ctx &c, int lane) {
     const double *jd = c.D + H[H_D_JOINT] + k * JD_STRIDE;
     st4(s + H[R_LQ] + k * 4, qmul(ld4(jd + JD_ORIGIN + 3), qangleaxis(q, ld3(jd + JD_AXIS))));
   }
-  if (lane == 31) {
+}
+// simulator step, body (one lane per rollout): integrates the dynamic body and poses the object link
+RL_HD void phaseBody(const Ctx &c) {
+  const int32_t *H = c.H;
+  const double *dc = dconst(c);
+  double *s = c.s;
+  {
     BodyStep b;
     double *body = s + H[R_BODY];
     for (int e = 0; e < B_COUNT; e++) s[H[R_BODY0] + e] = body[e];  // the adjoint restarts from here
@@ -214,28 +221,60 @@ RL_HD void phaseSim(const Ctx &c, int lane) {
   }
 }
 
-// forward kinematics, one super-level: every lane walks one serial segment of the tree with the running pose
-// in registers, pose = parent * (origin.t, local rotation) joint after joint
-RL_HD void phaseChain(const Ctx &c, int lane, int super) {
+// ---- forward kinematics (pose = parent * (origin.t, local rotation), robotmodel.h:128-148; the reference rotates
+// about the joint axis after composing parent * origin, see the header comment) as warp scans (rollout_plan.h, RD_*): one warp owns one rollout, a lane per joint
+// of a *round*; the chain products and sums inside a segment are prefix scans over the lanes.  Written over N lanes
+// at once with the lane exchange as a policy: N = 1 and warp shuffles on the device (trx_rollout.cu), N = 32 and
+// array shifts in the host emulation (tests/emu/rollout_emu.cpp) -- same statements, same order.
+//   W::up(x, d, o):   o[lane] = x[lane - d]   (lanes below d keep their own value)
+//   W::down(x, d, o): o[lane] = x[lane + d]
+struct RoundLane {
+  int k, j, len, par;
+};
+RL_HD RoundLane roundLane(const Ctx &c, int round, int lane) {
+  const int32_t *rd = c.I + c.H[H_I_ROUND] + (round * 32 + lane) * RD_STRIDE;
+  return RoundLane{rd[RD_K], rd[RD_J], rd[RD_LEN], rd[RD_PAR]};
+}
+
+template <int N, class W> RL_HD void fkRoundForward(const Ctx &c, int round, int lane0) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  const int s0 = I[H[H_I_SUPER] + super - 1], s1 = I[H[H_I_SUPER] + super];
-  for (int sg = s0 + lane; sg < s1; sg += 32) {
-    const int k0 = I[H[H_I_SEG] + 2 * sg], n = I[H[H_I_SEG] + 2 * sg + 1];
-    PoseV p = ldp(s + H[R_POSE] + I[H[H_I_JOINT] + k0 * JI_STRIDE + JI_PARENT] * 7);
-    const double *jd = c.D + H[H_D_JOINT] + k0 * JD_STRIDE;
-    const double *lq = s + H[R_LQ] + k0 * 4;
-    double *out = s + H[R_POSE] + k0 * 7;
-    for (int j = 0; j < n; j++, jd += JD_STRIDE, lq += 4, out += 7) {
-      p.t = p.t + qrot(p.r, ld3(jd + JD_ORIGIN));
-      p.r = qmul(p.r, ld4(lq));
-      stp(out, p);
-    }
+  const int steps = I[H[H_I_ROUNDSTEPS] + round];
+  RoundLane rl[N];
+  Q4 q[N], o4[N], r[N];
+  V3 a[N], o3[N];
+  PoseV pp[N];
+  for (int i = 0; i < N; i++) {
+    rl[i] = roundLane(c, round, lane0 + i);
+    const bool on = rl[i].k >= 0;
+    q[i] = on ? ld4(s + H[R_LQ] + rl[i].k * 4) : Q4{0, 0, 0, 1};
+    pp[i] = on ? ldp(s + H[R_POSE] + rl[i].par * 7) : PoseV{{0, 0, 0}, {0, 0, 0, 1}};
   }
+  // q_j = l_0 * l_1 * ... * l_j  (local rotations of the segment up to this joint)
+  for (int st = 0, d = 1; st < steps; st++, d <<= 1) {
+    W::up(q, d, o4);
+    for (int i = 0; i < N; i++)
+      if (rl[i].j >= d) q[i] = qmul(o4[i], q[i]);
+  }
+  for (int i = 0; i < N; i++) r[i] = qmul(pp[i].r, q[i]);
+  // arm of joint j: rotation of its parent (the lane below, or the segment's parent) applied to its origin
+  W::up(r, 1, o4);
+  for (int i = 0; i < N; i++) {
+    const Q4 rpar = rl[i].j == 0 ? pp[i].r : o4[i];
+    a[i] = rl[i].k >= 0 ? qrot(rpar, ld3(c.D + H[H_D_JOINT] + rl[i].k * JD_STRIDE + JD_ORIGIN)) : V3{0, 0, 0};
+  }
+  for (int st = 0, d = 1; st < steps; st++, d <<= 1) {
+    W::up(a, d, o3);
+    for (int i = 0; i < N; i++)
+      if (rl[i].j >= d) a[i] = o3[i] + a[i];
+  }
+  for (int i = 0; i < N; i++)
+    if (rl[i].k >= 0) stp(s + H[R_POSE] + rl[i].k * 7, PoseV{pp[i].t + a[i], r[i]});
 }
 
 // joint-limit penalties (dexlearn.h:139-157) and the policy input (dexenv_grasp.h:50-121)
-RL_HD void phaseObserve(const Ctx &c, int lane, int frame, double &loss) {
+// kEmit = false: values only (the adjoint sweep recomputes a frame without counting its residual rows again)
+template <bool kEmit> RL_HD void phaseObserve(const Ctx &c, int lane, int frame, double &loss) {
   const int32_t *I = c.I, *H = c.H;
   const double *dc = dconst(c);
   double *s = c.s;
@@ -244,8 +283,10 @@ RL_HD void phaseObserve(const Ctx &c, int lane, int frame, double &loss) {
   for (int ci = lane; ci < nq; ci += 32) {
     const double *cd = c.D + H[H_D_CTRL] + ci * CD_STRIDE;
     const double q = s[H[R_Q] + ci], w = dc[DC_W_JLIMIT];
-    emit(c, row0 + 2 * ci, relu(q - cd[CD_UPPER]) * w, loss);
-    emit(c, row0 + 2 * ci + 1, relu(cd[CD_LOWER] - q) * w, loss);
+    if (kEmit) {
+      emit(c, row0 + 2 * ci, relu(q - cd[CD_UPPER]) * w, loss);
+      emit(c, row0 + 2 * ci + 1, relu(cd[CD_LOWER] - q) * w, loss);
+    }
     if (H[H_NLAYERS]) c.x[ci] = q;
   }
   if (lane == 31 && H[H_NLAYERS]) {
@@ -360,7 +401,7 @@ RL_HD Side sideOf(const Ctx &c, int item, int frame) {
 }
 
 // contacts, step 1 (dexlearn.h:250-283): contact point of one side, its regularisation and shape penalty
-RL_HD void phaseContact1(const Ctx &c, int lane, int frame, double &loss) {
+template <bool kEmit> RL_HD void phaseContact1(const Ctx &c, int lane, int frame, double &loss) {
   const int32_t *I = c.I, *H = c.H;
   const double *dc = dconst(c);
   double *s = c.s;
@@ -370,13 +411,15 @@ RL_HD void phaseContact1(const Ctx &c, int lane, int frame, double &loss) {
     const double *cp = c.out + nq + sd.e * H[H_CDIMS] + sd.side * 3;
     const V3 cs = ld3(cp) * 0.1;
     const V3 reg = cs * dc[DC_W_CPR];
-    emit(c, sd.row_ee + sd.side * 3 + 0, reg.x, loss);
-    emit(c, sd.row_ee + sd.side * 3 + 1, reg.y, loss);
-    emit(c, sd.row_ee + sd.side * 3 + 2, reg.z, loss);
+    if (kEmit) {
+      emit(c, sd.row_ee + sd.side * 3 + 0, reg.x, loss);
+      emit(c, sd.row_ee + sd.side * 3 + 1, reg.y, loss);
+      emit(c, sd.row_ee + sd.side * 3 + 2, reg.z, loss);
+    }
     const PoseV pose = ldp(s + H[R_POSE] + sd.link * 7);
     const V3 pt = pmulv(pose, ld3(sd.sd + ED_CENTER)) + cs;
     st3(s + H[R_EE] + sd.e * EE_STRIDE + (sd.side ? EE_C2 : EE_C1), pt);
-    if (c.emit) {
+    if (kEmit) {
       const V3 local = pmulv(pinv(pose), pt);
       shapeRows<false>(c, sd.si, sd.sd, local, sd.row_shape, loss);
     }
@@ -508,16 +551,11 @@ RL_HD void phaseInit(const Ctx &c, int lane, const double *params) {
 RL_HD void bphaseBegin(const Ctx &c, int lane, int frame) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  const int nj = H[H_NJ];
-  for (int e = lane; e < nj * 6; e += 32) {
-    const int k = e / 6;
-    const int t = I[H[H_I_JOINT] + k * JI_STRIDE + JI_TRACK];
-    double g = 0.0;
-    if (t >= 0) {
-      g = s[H[R_GPREV] + t * 6 + (e - k * 6)];
-      s[H[R_GPREV] + t * 6 + (e - k * 6)] = 0.0;  // refilled by this frame's slip velocities
-    }
-    s[H[R_GPOSE] + e] = g;
+  // every other link-pose adjoint is zero: its consumer (bphaseChainWrench, the body lane of bphaseSim) cleared it
+  for (int e = lane; e < H[H_NTRACK] * 6; e += 32) {
+    const int t = e / 6, k = I[H[H_I_TRACK] + t];
+    s[H[R_GPOSE] + k * 6 + (e - t * 6)] = s[H[R_GPREV] + e];
+    s[H[R_GPREV] + e] = 0.0;  // refilled by this frame's slip velocities
   }
 }
 RL_HD void bphaseBegin2(const Ctx &c, int lane, int frame) {
@@ -685,10 +723,11 @@ RL_HD void bphaseControl(const Ctx &c, int lane, int frame) {
     const double o = c.out[i];
     const double gs = seedOf(c, row0 + i, o * creg) * creg;
     if (i < nq) {
+      // the command of joint i and, with the J1 := J2 coupling, of the joint it also drives (dexenv_grasp.h:200-219)
       double g_vel = 0;
-      for (int ci = 0; ci < nq; ci++)
-        if (I[H[H_I_CTRL] + ci * CI_STRIDE + CI_SRC] == i)
-          g_vel += s[H[R_GCMD] + ci] * c.D[H[H_D_CTRL] + ci * CD_STRIDE + CD_SCALE];
+      const int32_t *cidx = I + H[H_I_CTRL] + i * CI_STRIDE;
+      if (cidx[CI_SRC] == i) g_vel += s[H[R_GCMD] + i] * c.D[H[H_D_CTRL] + i * CD_STRIDE + CD_SCALE];
+      if (cidx[CI_DST] >= 0) g_vel += s[H[R_GCMD] + cidx[CI_DST]] * c.D[H[H_D_CTRL] + cidx[CI_DST] * CD_STRIDE + CD_SCALE];
       const double v = s[H[R_VEL] + i];
       c.gout[i] = g_vel * (1.0 - v * v) + gs;  // prepare_tanh saves 1 - x^2
     } else {
@@ -734,57 +773,94 @@ RL_HD void bphaseObserve(const Ctx &c, int lane, int frame) {
     const V3 g_rel = ld3(gx + 9);
     g_obj.t = g_obj.t - g_rel;
     add3(s + H[R_GPOSE] + H[H_PALM] * 6, g_rel);
-    for (int e = 0; e < H[H_NEE]; e++) {
-      g_obj.t = g_obj.t + ld3(s + H[R_GOBJ] + e * 6);
-      g_obj.r = g_obj.r + ld3(s + H[R_GOBJ] + e * 6 + 3);
-    }
     addt(s + H[R_GPOSE] + H[H_OBJ] * 6, g_obj);
-    const int ot = I[H[H_I_OBJSHAPE] + EI_TRACK];
-    for (int e = 0; e < H[H_NEE]; e++) addt(s + H[R_GPREV] + ot * 6, ldt(s + H[R_GPREVOBJ] + e * 6));
   }
 }
-
-// adjoint of the forward kinematics, one super-level (deepest first): a lane walks its segment from the last
-// joint to the first; a joint collects what its own link and the segments hanging off it left, takes its angle's
-// share and hands the rest up
-// (reverse_mul_fg_pose: da = (dx.t, cross(qrot(a.r, b.t), dx.t) + dx.r);
-//  reverse_fg_pose_angle_axis_pose: dangle = dot(qrot(qinv(parent.r), dp.r), axis))
-RL_HD void bphaseChain(const Ctx &c, int lane, int super) {
+// what the end effectors left for the object link and for its previous pose (one slot per end effector, because
+// all of them touch the same link): summed component by component, lanes 0..5 the pose adjoint, 6..11 the previous
+RL_HD void bphaseObjectGather(const Ctx &c, int lane) {
   const int32_t *I = c.I, *H = c.H;
   double *s = c.s;
-  const int s0 = I[H[H_I_SUPER] + super - 1], s1 = I[H[H_I_SUPER] + super];
-  for (int sg = s0 + lane; sg < s1; sg += 32) {
-    const int k0 = I[H[H_I_SEG] + 2 * sg], n = I[H[H_I_SEG] + 2 * sg + 1];
-    TwistV carry{{0, 0, 0}, {0, 0, 0}};
-    for (int k = k0 + n - 1; k >= k0; k--) {
-      const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
-      TwistV g = ldt(s + H[R_GPOSE] + k * 6);
-      g.t = g.t + carry.t;
-      g.r = g.r + carry.r;
-      for (int ch = 0; ch < ji[JI_NCHILD]; ch++) {
-        const TwistV gc = ldt(s + H[R_GC] + I[ji[JI_CHILD0] + ch] * 6);
-        g.t = g.t + gc.t;
-        g.r = g.r + gc.r;
-      }
-      const PoseV parent = ldp(s + H[R_POSE] + (k > k0 ? k - 1 : ji[JI_PARENT]) * 7);
-      const V3 arm = ld3(s + H[R_POSE] + k * 7) - parent.t;  // = qrot(parent.r, origin.t)
-      carry = TwistV{g.t, cross(arm, g.t) + g.r};
-      // fixed joints carry a zero axis and the spare slot n_q
-      s[H[R_GQ] + ji[JI_CTRL]] += dot(qrot(qinv(parent.r), g.r), ld3(c.D + H[H_D_JOINT] + k * JD_STRIDE + JD_CAXIS));
-    }
-    stt(s + H[R_GC] + k0 * 6, carry);
-  }
+  if (lane >= 12 || !H[H_NLAYERS]) return;
+  const int comp = lane < 6 ? lane : lane - 6;
+  const double *src = s + (lane < 6 ? H[R_GOBJ] : H[R_GPREVOBJ]) + comp;
+  double sum = 0.0;
+  for (int e = 0; e < H[H_NEE]; e++) sum += src[e * 6];
+  if (lane < 6) s[H[R_GPOSE] + H[H_OBJ] * 6 + comp] += sum;
+  else s[H[R_GPREV] + I[H[H_I_OBJSHAPE] + EI_TRACK] * 6 + comp] += sum;
 }
 
-// adjoint of the simulator step: velocity controllers (lanes < n_q) and the body (lane 31)
-RL_HD void bphaseSim(const Ctx &c, int lane) {
+// adjoint of the forward kinematics.  What a joint hands to its parent is (g.t, cross(p_k - p_parent, g.t) + g.r)
+// (reverse_mul_fg_pose: da = (dx.t, cross(qrot(a.r, b.t), dx.t) + dx.r)): force and torque of a wrench moved from the
+// joint's origin to the parent's.  Referred to the world origin instead, moving is the identity, so the total a
+// joint sees is a plain sum over its subtree; the joint angle takes the torque about its own origin,
+// M_k - cross(p_k, F_k), through reverse_fg_pose_angle_axis_pose: dangle = dot(qrot(qinv(parent.r), torque), axis).
+// Same terms as a joint-by-joint walk, summed in a different order.
+// the adjoint of the forward kinematics as warp scans, one round (deepest first): wrench of every joint about the
+// world origin plus what the segments hanging off it collected, suffix sums inside the segments, joint angles
+template <int N, class W> RL_HD void fkRoundReverse(const Ctx &c, int round, int lane0) {
   const int32_t *I = c.I, *H = c.H;
+  double *s = c.s;
+  const int steps = I[H[H_I_ROUNDSTEPS] + round];
+  RoundLane rl[N];
+  TwistV w[N], o[N];
+  V3 p[N];
+  for (int i = 0; i < N; i++) {
+    rl[i] = roundLane(c, round, lane0 + i);
+    w[i] = TwistV{{0, 0, 0}, {0, 0, 0}};
+    p[i] = V3{0, 0, 0};
+    if (rl[i].k < 0) continue;
+    const int k = rl[i].k;
+    double *gp = s + H[R_GPOSE] + k * 6;
+    const TwistV g = ldt(gp);
+    stt(gp, TwistV{{0, 0, 0}, {0, 0, 0}});
+    p[i] = ld3(s + H[R_POSE] + k * 7);
+    w[i] = TwistV{g.t, g.r + cross(p[i], g.t)};
+    const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
+    for (int ch = 0; ch < ji[JI_NCHILD]; ch++) {
+      const TwistV gc = ldt(s + H[R_GC] + I[ji[JI_CHILD0] + ch] * 6);
+      w[i].t = w[i].t + gc.t;
+      w[i].r = w[i].r + gc.r;
+    }
+  }
+  for (int st = 0, d = 1; st < steps; st++, d <<= 1) {
+    W::down(w, d, o);
+    for (int i = 0; i < N; i++)
+      if (rl[i].j + d < rl[i].len) {
+        w[i].t = w[i].t + o[i].t;
+        w[i].r = w[i].r + o[i].r;
+      }
+  }
+  for (int i = 0; i < N; i++) {
+    if (rl[i].k < 0) continue;
+    const int k = rl[i].k;
+    if (rl[i].j == 0) stt(s + H[R_GC] + k * 6, w[i]);  // the segment's total, for the joint it hangs off
+    const int32_t *ji = I + H[H_I_JOINT] + k * JI_STRIDE;
+    if (ji[JI_TYPE] != dexsyn::JOINT_REVOLUTE) continue;
+    const V3 torque = w[i].r - cross(p[i], w[i].t);
+    const Q4 rpar = ld4(s + H[R_POSE] + ji[JI_PARENT] * 7 + 3);
+    s[H[R_GQ] + ji[JI_CTRL]] += dot(qrot(qinv(rpar), torque), ld3(c.D + H[H_D_JOINT] + k * JD_STRIDE + JD_CAXIS));
+  }
+}
+// pose adjoints of the links outside the segments (statics: the floor collects contact adjoints nobody reads);
+// the object's is consumed and cleared by the body lane of bphaseSim
+RL_HD void fkClearStatics(const Ctx &c, int lane) {
+  const int32_t *H = c.H;
+  for (int k = lane; k < H[H_KSEG0]; k += 32)
+    if (k != H[H_OBJ]) stt(c.s + H[R_GPOSE] + k * 6, TwistV{{0, 0, 0}, {0, 0, 0}});
+}
+
+// adjoint of the simulator step, joints: q = q_prev + cmd_prev * dt   (reverse_add, reverse_mul with a constant)
+RL_HD void bphaseSim(const Ctx &c, int lane) {
+  const int32_t *H = c.H;
+  const double dt = dconst(c)[DC_DT];
+  for (int ci = lane; ci < H[H_NQ]; ci += 32) c.s[H[R_GCMD] + ci] = c.s[H[R_GQ] + ci] * dt;
+}
+// adjoint of the simulator step, body (one lane per rollout)
+RL_HD void bphaseBody(const Ctx &c) {
+  const int32_t *H = c.H;
   const double *dc = dconst(c);
   double *s = c.s;
-  const int nq = H[H_NQ];
-  // q = q_prev + cmd_prev * dt   (reverse_add, reverse_mul with a constant)
-  for (int ci = lane; ci < nq; ci += 32) s[H[R_GCMD] + ci] = s[H[R_GQ] + ci] * dc[DC_DT];
-  if (lane != 31) return;
   BodyStep b;
   bodyForward(dc, s + H[R_BODY0], b);
   const double dt = dc[DC_DT];
@@ -795,6 +871,7 @@ RL_HD void bphaseSim(const Ctx &c, int lane) {
   for (int e = 0; e < H[H_NEE]; e++) g_cg = g_cg + ld3(s + H[R_EE] + e * EE_STRIDE + EE_GP);
   // object link pose D = C * R(fo), C = origin * T(fp); fp, fo = translation / orientation of Bp
   const TwistV g_D = ldt(s + H[R_GPOSE] + H[H_OBJ] * 6);
+  stt(s + H[R_GPOSE] + H[H_OBJ] * 6, TwistV{{0, 0, 0}, {0, 0, 0}});
   const V3 g_C_t = g_D.t;                                    // reverse_mul_fg_pose da.t (b.t = 0: no lever arm)
   const V3 g_fo = qrot(qinv(b.C.r), g_D.r);                  // db.r -> reverse_fg_orientation_pose
   const PoseV org = ldp(dc + DC_OBJ_ORIGIN);
@@ -851,6 +928,7 @@ RL_HD void bphaseInit(const Ctx &c, int lane) {
   for (int e = lane; e < GB_COUNT; e += 32) s[H[R_GBODY] + e] = 0.0;
   for (int e = lane; e < H[H_NTRACK] * 6; e += 32) s[H[R_GPREV] + e] = 0.0;
   for (int e = lane; e < 6; e += 32) s[H[R_GFIRST] + e] = 0.0;
+  for (int e = lane; e < H[H_NJ] * 6; e += 32) s[H[R_GPOSE] + e] = 0.0;
 }
 
 }  // namespace rollout

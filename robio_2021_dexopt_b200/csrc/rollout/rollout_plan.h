@@ -33,6 +33,7 @@ namespace rollout {
 enum {
   H_NJ = 0,       // joints in the pruned pose table (level order; statics first)
   H_NSTATIC,      // leading joints whose pose is a constant
+  H_KSEG0,        // first joint of the segments (statics and floating joints come before)
   H_NSUPER,       // super-levels of the segment tree
   H_NSEG,         // segments
   H_NQ,           // controlled (revolute) joints
@@ -58,6 +59,9 @@ enum {
   H_I_EE,         // [n_ee * EI_STRIDE]
   H_I_TRACK,      // [n_track] pose-table index
   H_I_OBJSHAPE,   // [EI_STRIDE] (link = object)
+  H_NROUND,       // warp rounds of the forward kinematics (below)
+  H_I_ROUND,      // [n_round][32 lanes][RD_STRIDE]; offset is a multiple of 4
+  H_I_ROUNDSTEPS, // [n_round] scan steps: ceil(log2(longest segment of the round))
   // offsets of double tables
   H_D_JOINT,      // [nj * JD_STRIDE]
   H_D_CTRL,       // [nq * CD_STRIDE]
@@ -77,8 +81,14 @@ enum { JI_PARENT = 0, JI_TYPE, JI_CTRL, JI_CHILD0, JI_NCHILD, JI_TRACK, JI_STRID
 // per joint, doubles: origin pose, axis in the joint frame, axis in the parent frame (R_origin * axis)
 enum { JD_ORIGIN = 0, JD_AXIS = 7, JD_CAXIS = 10, JD_STRIDE = 13 };
 // per controlled joint
-enum { CI_JOINT = 0, CI_SRC, CI_STRIDE };  // SRC: policy output whose tanh drives it (J1 := J2 coupling)
+// SRC: policy output whose tanh drives it (J1 := J2 coupling); DST: the other joint this output drives (-1: none)
+enum { CI_JOINT = 0, CI_SRC, CI_DST, CI_STRIDE };
 enum { CD_LOWER = 0, CD_UPPER, CD_Q0, CD_SCALE, CD_STRIDE };
+// Forward kinematics as warp scans: the segments of one super-level are packed side by side into the 32 lanes of a
+// *round* (a lane per joint); inside a segment the chain products / sums are prefix scans over the lanes, so a
+// serial chain of n joints costs log2(n) steps.  Per lane: joint (-1: idle lane), position inside its segment,
+// segment length, parent joint of the segment's first joint.
+enum { RD_K = 0, RD_J, RD_LEN, RD_PAR, RD_STRIDE };
 // per end effector / shape
 enum { EI_LINK = 0, EI_KIND, EI_NPLANES, EI_PLANE0, EI_NROWS, EI_TRACK, EI_ROW, EI_STRIDE };
 enum { ED_CENTER = 0, ED_RADIUS = 3, ED_LENGTH, ED_STRIDE };
@@ -222,6 +232,9 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   auto &D = p.d;
   I[H_NJ] = nj;
   I[H_NSTATIC] = n_static;
+  I[H_KSEG0] = nj;
+  for (auto &sg : segs)
+    for (int j : sg.joints) I[H_KSEG0] = std::min(I[H_KSEG0], index[j]);
   I[H_NSUPER] = n_super;
   I[H_NSEG] = (int)segs.size();
   I[H_NQ] = nq;
@@ -314,9 +327,68 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     const auto &jt = m.joints[m.controlled[c]];
     I.push_back(index[m.controlled[c]]);
     I.push_back(jt.couple_to >= 0 ? m.joints[jt.couple_to].control : c);
+    I.push_back(-1);
+  }
+  for (int c = 0; c < nq; c++) {
+    const int src = I[I[H_I_CTRL] + c * CI_STRIDE + CI_SRC];
+    if (src == c) continue;
+    int &dst = I[I[H_I_CTRL] + src * CI_STRIDE + CI_DST];
+    if (dst >= 0 || I[I[H_I_CTRL] + src * CI_STRIDE + CI_SRC] != src) {
+      p.error = "joint coupling is not one-to-one";
+      return p;
+    }
+    dst = c;
   }
   I[H_I_TRACK] = (int)I.size();
   for (int t : track) I.push_back(t);
+  {
+    // warp rounds: super-levels in order, segments first-fit into rounds of 32 lanes
+    std::vector<int32_t> rounds, steps;
+    int lane = 32, longest = 0;
+    auto closeRound = [&]() {
+      if (lane == 32 && rounds.empty()) return;
+      int st = 0;
+      while ((1 << st) < longest) st++;
+      steps.push_back(st);
+    };
+    int cur_super = -1;
+    for (auto &sg : segs) {
+      const int n = (int)sg.joints.size();
+      if (n > 32) {
+        p.error = "a serial run of more than 32 joints";
+        return p;
+      }
+      if (sg.super != cur_super || lane + n > 32) {
+        if (!rounds.empty()) closeRound();
+        rounds.resize(rounds.size() + 32 * RD_STRIDE, 0);
+        for (int l = 0; l < 32; l++) rounds[rounds.size() - 32 * RD_STRIDE + l * RD_STRIDE + RD_K] = -1;
+        lane = 0;
+        longest = 0;
+        cur_super = sg.super;
+      }
+      const int par = m.joints[sg.joints.front()].parent;
+      for (int j = 0; j < n; j++, lane++) {
+        int32_t *rd = &rounds[rounds.size() - 32 * RD_STRIDE + lane * RD_STRIDE];
+        rd[RD_K] = index[sg.joints[j]];
+        rd[RD_J] = j;
+        rd[RD_LEN] = n;
+        rd[RD_PAR] = par >= 0 ? index[par] : -1;
+      }
+      longest = std::max(longest, n);
+    }
+    if (!rounds.empty()) closeRound();
+    for (auto &sg : segs)
+      if (m.joints[sg.joints.front()].parent < 0) {
+        p.error = "moving joint attached to the world";  // not produced by dexsyn::makeModel (the base link is fixed)
+        return p;
+      }
+    while (I.size() % 4) I.push_back(0);
+    I[H_NROUND] = (int)steps.size();
+    I[H_I_ROUND] = (int)I.size();
+    I.insert(I.end(), rounds.begin(), rounds.end());
+    I[H_I_ROUNDSTEPS] = (int)I.size();
+    I.insert(I.end(), steps.begin(), steps.end());
+  }
 
   // ---- double tables
   D.clear();
@@ -480,7 +552,10 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   take(R_GOBJ, n_ee * 6);
   take(R_GPREVOBJ, n_ee * 6);
   take(R_BODY0, B_COUNT);
+  // region stride == 2 (mod 16) doubles: the kernel's lanes hold the same item of 8 rollouts (trx_rollout.cu), so
+  // a half warp reads one offset of 8 regions plus the next item's -- distinct 8-byte banks
   I[H_REGION] = padTo(off, 2);
+  while (I[H_REGION] % 16 != 2) I[H_REGION] += 2;
   // checkpoint: joint positions, commands, body state, tracked previous poses
   I[H_CKPT] = nq + nq + B_COUNT + n_track * 7;
   return p;

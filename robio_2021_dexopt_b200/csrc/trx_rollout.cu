@@ -13,10 +13,12 @@
 //   reverse_batch lane sums (dexopt/src/ops.h:22-34)   dW = X^T G accumulated in registers over all frames and
 //                                                      rollouts of the CTA, one deterministic cross-CTA sum at the end
 //
-// Mapping: a CTA holds NW rollouts, one warp each (lane = joint / policy output / contact side inside a
-// phase, __syncwarp between phases); at the policy layers the NW warps turn into tile workers of one
-// [8 x n_in] x [n_in x n_out] product (M = the rollouts).  HBM sees the checkpoint (written once, read once),
-// the weights (once per CTA) and the per-CTA partial gradient.
+// Mapping: a CTA works on a group of NW = 8 rollouts with 8 main warps and 8 helper warps (kernel comment below).
+// Main warps run the frame phases with thread = (rollout, item slot) -- the lanes of a warp hold the same item of
+// the 8 rollouts -- the forward kinematics and its adjoint as warp scans (warp = rollout), and the policy layers as
+// tile workers of one [8 x n_in] x [n_in x n_out] product (M = the rollouts).  Helper warps take what is off the
+// frame's critical path: the body step and its adjoint, and the weight gradients.  HBM sees the checkpoint
+// (written once, read once), the weights (once per CTA) and the per-CTA partial gradient.
 //
 // sm_100a only; no CPU path.
 #include <cuda_runtime.h>
@@ -59,7 +61,8 @@ struct KArgs {
   int o_D, o_I, o_W1, o_B1, o_W2, o_B2, s_W1, s_W2, r_W1, r_W2;
   int o_X, o_H, o_A, o_O, o_GX, o_GH, o_GO, s_X, s_H, s_O;
   int o_tile, o_red, o_region;
-  int n_tiles, tiles_j1, tiles_1;  // dW tiles: [0, tiles_1) layer 1, rest layer 2
+  int o_zero;                      // 8 rows of zeros at the widest activation stride: operands of padding tiles
+  int tiles_j1, tiles_1, tiles_jl, tiles_l;  // dW tiles of the first layer (two-layer policies) and of the last layer
 };
 
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): g = lane >> 2, t = lane & 3;
@@ -127,17 +130,51 @@ __device__ long long g_rollout_prof[64];
   { __VA_ARGS__; }
 #endif
 
-template <int NW, int MAXT>
-__global__ void __launch_bounds__(NW * 32, 1)
+// lane exchange of the warp-scan phases (rollout_frame.h fkRound*): shuffles, component by component
+struct DeviceWarp {
+  template <class T> static __device__ __forceinline__ void up(const T (&x)[1], int d, T (&o)[1]) {
+    const double *src = reinterpret_cast<const double *>(&x[0]);
+    double *dst = reinterpret_cast<double *>(&o[0]);
+#pragma unroll
+    for (int e = 0; e < (int)(sizeof(T) / sizeof(double)); e++) dst[e] = __shfl_up_sync(0xffffffffu, src[e], d);
+  }
+  template <class T> static __device__ __forceinline__ void down(const T (&x)[1], int d, T (&o)[1]) {
+    const double *src = reinterpret_cast<const double *>(&x[0]);
+    double *dst = reinterpret_cast<double *>(&o[0]);
+#pragma unroll
+    for (int e = 0; e < (int)(sizeof(T) / sizeof(double)); e++) dst[e] = __shfl_down_sync(0xffffffffu, src[e], d);
+  }
+};
+
+// block barriers: all warps of the CTA, or the NW main warps only (named barrier 1)
+__device__ __forceinline__ void barAll() { __syncthreads(); }
+template <int NTHREADS> __device__ __forceinline__ void barMain() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+}
+
+constexpr int kHelperWarps = 8;            // helper warps of a CTA:
+constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one body warp
+
+// One CTA = one group of NW rollouts at a time, NW main warps + 4 helper warps:
+//   main warps     the frame phases (rollout_frame.h), the policy layers and their input adjoints (DMMA tiles)
+//   helper warps   what is off the frame's critical path: the body step and its adjoint (helper warp 0, a lane per
+//                  rollout) while the main warps run the forward kinematics, and the weight gradients dW = X^T GY
+//                  (register accumulators: U1 tiles of the first layer of a two-layer policy and UL tiles of the
+//                  last layer per helper warp, over all frames and groups of the CTA) plus the bias gradients
+//                  while the main warps go on with the adjoint of the frame.
+// The two sides meet at the full barriers A..G of a step; everything else synchronises the main warps only.
+template <int NW, int U1, int UL>
+__global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
     trx_rollout_kernel(const __grid_constant__ KHeader hdr, const __grid_constant__ KArgs a) {
   extern __shared__ double sm[];
   const int32_t *H = hdr.v;
-  const int tid = threadIdx.x, nt = NW * 32, warp = tid >> 5, lane = tid & 31;
+  constexpr int NH = kHelperWarps, NHD = kDwWarps, NTM = NW * 32, NTH = NH * 32, NTD = NHD * 32, MAXT = U1 + UL;
+  const int tid = threadIdx.x, nt = NTM + NTH, warp = tid >> 5, lane = tid & 31;
 #ifdef TRX_ROLLOUT_PROFILE
   __shared__ long long sprof[64];
   if (tid < 64) sprof[tid] = 0;
 #endif
-  const int n_in = H[H_NIN], n_hid = H[H_NHID], n_out = H[H_NOUT], n_layers = H[H_NLAYERS], L = H[H_NSUPER];
+  const int n_in = H[H_NIN], n_hid = H[H_NHID], n_out = H[H_NOUT], n_layers = H[H_NLAYERS];
   const int n1 = n_layers == 2 ? n_hid : n_out;  // output width of the first layer
 
   // ---- stage the plan and the weights
@@ -163,56 +200,204 @@ __global__ void __launch_bounds__(NW * 32, 1)
       for (int e = tid; e < n_out; e += nt) sm[a.o_B2 + e] = B2[e];
     }
   }
-  // dW tile table: per tile {offset of the A operand column block, offset of the B operand column block}
-  int32_t *tile_tab = reinterpret_cast<int32_t *>(sm + a.o_tile);
-  for (int tl = tid; tl < a.n_tiles; tl += nt) {
-    int ti, tj, xo, yo;
-    if (tl < a.tiles_1) {
-      ti = tl / a.tiles_j1, tj = tl - ti * a.tiles_j1;
-      xo = a.o_X, yo = n_layers == 2 ? a.o_GH : a.o_GO;
+  // dW tile table, [dW warp][U1 + UL] entries {A operand column block, B operand column block} (offsets in
+  // doubles): tile idx = dW warp + u * NHD of its layer; slots past the layer's tile count point both operands
+  // at zeros, so the accumulation is straight-line code without a test per tile
+  int2 *tile_tab = reinterpret_cast<int2 *>(sm + a.o_tile);
+  for (int e = tid; e < NHD * MAXT; e += nt) {
+    const int w = e / MAXT, u = e - w * MAXT;
+    int2 ent = make_int2(a.o_zero, a.o_zero);
+    if (u < U1) {
+      const int idx = w + u * NHD;
+      if (n_layers == 2 && idx < a.tiles_1) ent = make_int2(a.o_X + (idx / a.tiles_j1) * 8, a.o_GH + (idx % a.tiles_j1) * 8);
     } else {
-      const int tiles_j2 = (n_out + 7) >> 3;
-      ti = (tl - a.tiles_1) / tiles_j2, tj = (tl - a.tiles_1) - ti * tiles_j2;
-      xo = a.o_A, yo = a.o_GO;
+      const int idx = w + (u - U1) * NHD;
+      if (idx < a.tiles_l)
+        ent = make_int2((n_layers == 2 ? a.o_A : a.o_X) + (idx / a.tiles_jl) * 8, a.o_GO + (idx % a.tiles_jl) * 8);
     }
-    tile_tab[2 * tl] = xo + ti * 8;
-    tile_tab[2 * tl + 1] = yo + tj * 8;
+    tile_tab[e] = ent;
   }
   __syncthreads();
 
   const double *sW1 = sm + a.o_W1, *sB1 = sm + a.o_B1, *sW2 = sm + a.o_W2, *sB2 = sm + a.o_B2;
   double *XS = sm + a.o_X, *HS = sm + a.o_H, *AS = sm + a.o_A, *OS = sm + a.o_O;
   double *GXS = sm + a.o_GX, *GHS = sm + a.o_GH, *GOS = sm + a.o_GO;
-  const int k1 = (n_in + 3) & ~3, k2 = (n_hid + 3) & ~3;
+  const int T = a.frames, CK = H[H_CKPT];
+  const int n_steps = a.want_grad ? 2 * T : T;
+  double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
 
+  if (warp == NW + NHD) {
+    // ================================================================================ body warp
+    // lane = rollout of the group: the body step while the main warps run the forward kinematics, its adjoint
+    // while they run the adjoint of the forward kinematics
+    Ctx cb;
+    cb.H = H, cb.I = sI, cb.D = sD;
+    cb.s = sm + a.o_region + (lane & (NW - 1)) * H[H_REGION];
+    cb.frames = T;
+    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      const bool body_lane = lane < (int)min((long)NW, a.count - (long)grp * NW);
+      barAll();  // the group starts
+      for (int step = 0; step <= n_steps; step++) {
+        if ((step == T && !a.want_grad) || step == n_steps) break;
+        barAll();  // A: the frame's carried state is in place
+        if (body_lane) phaseBody(cb);
+        barAll();  // B
+        if (step < T) continue;
+        barAll();  // C
+        barAll();  // D
+        barAll();  // E: the object's pose adjoint is complete
+        if (body_lane) bphaseBody(cb);
+        barAll();  // G: the frame is done
+      }
+    }
+    return;
+  }
+  if (warp >= NW) {
+    // ================================================================================ dW warps
+    const int hw = warp - NW, htid = tid - NTM;
+    const int gi = lane >> 2, t4 = lane & 3;
+    double acc[MAXT][2];
+#pragma unroll
+    for (int u = 0; u < MAXT; u++) acc[u][0] = acc[u][1] = 0.0;
+    double gb0 = 0.0, gb1 = 0.0;  // bias gradients: element htid and htid + NTD of {b1, b2}
+    // lane parts of the dW operand addresses: A[g][t] = X[rollout t][column g], B[t][g] = GY[rollout t][column g]
+    const int s_xl = n_layers == 2 ? a.s_H : a.s_X;  // last layer: X = activations of the hidden layer
+    const int2 *my_tiles = tile_tab + hw * MAXT;
+    for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
+      barAll();  // the group starts
+      for (int step = 0; step <= n_steps; step++) {
+        if ((step == T && !a.want_grad) || step == n_steps) break;
+        barAll();  // A
+        barAll();  // B
+        if (step < T) continue;
+        barAll();  // C: output adjoint of the last layer complete
+#ifdef TRX_ROLLOUT_PROFILE
+        long long _h0 = clock64();
+#endif
+        {
+          // dW += X^T GY, K = the 8 rollouts = two DMMAs per 8x8 tile; the first DMMA of every tile, then the
+          // second, so that consecutive DMMAs never wait on each other's accumulator
+          const double *xl = sm + gi + t4 * s_xl, *yl = sm + gi + t4 * a.s_O;
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int u = U1; u < MAXT; u++) {
+              const int2 tt = my_tiles[u];
+              dmma884(acc[u][0], acc[u][1], xl[tt.x + 4 * half * s_xl], yl[tt.y + 4 * half * a.s_O]);
+            }
+          }
+          const int base = n_layers == 2 ? n_hid : 0;
+          for (int e = htid, sl2 = 0; e < base + n_out; e += NTD, sl2++) {
+            if (e < base) continue;
+            const double *gy = GOS + (e - base);
+            double sgy = 0;
+            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_O];
+            if (sl2 == 0) gb0 += sgy;
+            else gb1 += sgy;
+          }
+        }
+#ifdef TRX_ROLLOUT_PROFILE
+        if (htid == 0) sprof[50] += clock64() - _h0;
+#endif
+        barAll();  // D: output adjoint of the first layer complete
+#ifdef TRX_ROLLOUT_PROFILE
+        _h0 = clock64();
+#endif
+        if (n_layers == 2) {
+          if (U1 > 0) {
+            const double *x1 = sm + gi + t4 * a.s_X, *y1 = sm + gi + t4 * a.s_H;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+              for (int u = 0; u < U1; u++) {
+                const int2 tt = my_tiles[u];
+                dmma884(acc[u][0], acc[u][1], x1[tt.x + 4 * half * a.s_X], y1[tt.y + 4 * half * a.s_H]);
+              }
+            }
+          }
+          for (int e = htid, sl2 = 0; e < n_hid; e += NTD, sl2++) {
+            const double *gy = GHS + e;
+            double sgy = 0;
+            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_H];
+            if (sl2 == 0) gb0 += sgy;
+            else gb1 += sgy;
+          }
+        }
+#ifdef TRX_ROLLOUT_PROFILE
+        if (htid == 0) sprof[51] += clock64() - _h0;
+#endif
+        barAll();  // E
+        barAll();  // G: the frame is done
+      }
+    }
+    // ---- this CTA's partial gradient
+    if (a.want_grad && n_layers) {
+#pragma unroll
+      for (int u = 0; u < MAXT; u++) {
+        int ti, tj, base, width, rows;
+        if (u < U1) {
+          const int idx = hw + u * NHD;
+          if (n_layers != 2 || idx >= a.tiles_1) continue;
+          ti = idx / a.tiles_j1, tj = idx - ti * a.tiles_j1;
+          base = H[H_W1], width = n1, rows = n_in;
+        } else {
+          const int idx = hw + (u - U1) * NHD;
+          if (idx >= a.tiles_l) continue;
+          ti = idx / a.tiles_jl, tj = idx - ti * a.tiles_jl;
+          base = n_layers == 2 ? H[H_W2] : H[H_W1], width = n_out, rows = n_layers == 2 ? n_hid : n_in;
+        }
+        const int i = ti * 8 + gi, j = tj * 8 + 2 * t4;
+        if (i < rows) {
+          double *p = part + 1 + base + i * width + j;
+          if (j < width) p[0] = a.accumulate ? p[0] + acc[u][0] : acc[u][0];
+          if (j + 1 < width) p[1] = a.accumulate ? p[1] + acc[u][1] : acc[u][1];
+        }
+      }
+      const int nb = (n_layers == 2 ? n_hid : 0) + n_out;
+      for (int e = htid, sl2 = 0; e < nb; e += NTD, sl2++) {
+        const double v = sl2 == 0 ? gb0 : gb1;
+        // {b1, b2} order; with one layer the only bias is b1
+        const int idx = n_layers == 2 ? (e < n_hid ? H[H_B1] + e : H[H_B2] + (e - n_hid)) : H[H_B1] + e;
+        part[1 + idx] = a.accumulate ? part[1 + idx] + v : v;
+      }
+    }
+    return;
+  }
+
+  // ================================================================================== main warps
+  const int k1 = (n_in + 3) & ~3, k2 = (n_hid + 3) & ~3;
+  // Work mapping outside the policy layers: thread = (rollout r of the CTA's group, slot); a phase with n items runs
+  // item = slot, slot + 32, ... of rollout r, so the lanes of a warp hold the SAME items of all NW rollouts.  Phases
+  // with few items (a dozen contact sides, six end effectors) then fill their warps across rollouts instead of
+  // issuing FP64 instructions for a few lanes per rollout (an FP64 warp instruction occupies the pipe for two cycles
+  // whatever its lane mask), and a phase's control flow is uniform across the lanes of an item.
+  const int r = tid & (NW - 1), slot = tid / NW;
   Ctx c;
   c.H = H;
   c.I = sI;
   c.D = sD;
-  c.s = sm + a.o_region + warp * H[H_REGION];
-  c.x = XS + warp * a.s_X, c.h = HS + warp * a.s_H, c.a = AS + warp * a.s_H, c.out = OS + warp * a.s_O;
-  c.gx = GXS + warp * a.s_X, c.gh = GHS + warp * a.s_H, c.gout = GOS + warp * a.s_O;
+  c.s = sm + a.o_region + r * H[H_REGION];
+  c.x = XS + r * a.s_X, c.h = HS + r * a.s_H, c.a = AS + r * a.s_H, c.out = OS + r * a.s_O;
+  c.gx = GXS + r * a.s_X, c.gh = GHS + r * a.s_H, c.gout = GOS + r * a.s_O;
   c.r_stride = a.R;
   c.frames = a.frames;
-  const int T = a.frames, CK = H[H_CKPT];
+  // The forward kinematics and its adjoint run with the other mapping: warp = rollout, lane = joint of a scan
+  // round (rollout_frame.h fkRound*); no block barrier inside them.
+  Ctx cw = c;
+  cw.s = sm + a.o_region + warp * H[H_REGION];
+  const int n_round = H[H_NROUND];
 
   double loss = 0.0;
-  double acc[MAXT > 0 ? MAXT : 1][2];
-#pragma unroll
-  for (int u = 0; u < (MAXT > 0 ? MAXT : 1); u++) acc[u][0] = acc[u][1] = 0.0;
-  double gb0 = 0.0, gb1 = 0.0;  // bias gradients: element tid and tid + nt of {b1, b2}
-
   const double w_reg = sD[H[H_D_CONST] + DC_W_REG], w_creg = sD[H[H_D_CONST] + DC_W_CREG];
   const int nq = H[H_NQ], rows_frame = H[H_ROWS_FRAME];
-  const int gi = lane >> 2, t4 = lane & 3;
-  constexpr int kPre = 6;  // checkpoint doubles per lane (H_CKPT <= 192, checked by the host)
+  constexpr int kPre = 6;  // checkpoint doubles per thread (H_CKPT <= 192, checked by the host)
   double pre[kPre];
 
   for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
     const long grp_first = (long)grp * NW;  // first rollout of the group inside this launch
     const int live = (int)min((long)NW, a.count - grp_first);  // rows of the group that are rollouts
-    const long local = grp_first + warp;
-    const bool active = warp < live;
+    const long local = grp_first + r;
+    const bool active = r < live;
     const long rollout = a.first + local;
     double *ckpt = a.ckpt + (size_t)local * T * CK;
     // element (row, g) of the group's residual rows / seeds at [row * R + g]
@@ -220,85 +405,81 @@ __global__ void __launch_bounds__(NW * 32, 1)
     const double *grp_seed = a.seed ? a.seed + H[H_NSCALAR] + a.first + grp_first : nullptr;
     c.r_out = (a.r_out && active) ? a.r_out + H[H_NSCALAR] + rollout : nullptr;
     c.seed = nullptr;
-    c.emit = true;
+    barAll();  // the group starts: everybody is done with the previous one
     if (!active) {
-      // an idle warp of the last group: its rows of the activation matrices must stay zero
-      for (int e = lane; e < a.s_X; e += 32) c.x[e] = 0.0, c.gx[e] = 0.0;
-      for (int e = lane; e < a.s_H; e += 32) c.h[e] = 0.0, c.a[e] = 0.0, c.gh[e] = 0.0;
-      for (int e = lane; e < a.s_O; e += 32) c.out[e] = 0.0, c.gout[e] = 0.0;
-    }
-    if (active) {
+      // an idle row of the last group: its rows of the activation matrices must stay zero
+      for (int e = slot; e < a.s_X; e += 32) c.x[e] = 0.0, c.gx[e] = 0.0;
+      for (int e = slot; e < a.s_H; e += 32) c.h[e] = 0.0, c.a[e] = 0.0, c.gh[e] = 0.0;
+      for (int e = slot; e < a.s_O; e += 32) c.out[e] = 0.0, c.gout[e] = 0.0;
+    } else {
       const double pr[3] = {a.params[rollout], a.params[a.R + rollout], a.params[2 * a.R + rollout]};
-      phaseInit(c, lane, pr);
-      __syncwarp();
-      for (int sl = 1; sl <= L; sl++) {
-        phaseChain(c, lane, sl);
+      phaseInit(c, slot, pr);
+    }
+    barMain<NTM>();
+    if (warp < live)
+      for (int rd = 0; rd < n_round; rd++) {
+        fkRoundForward<1, DeviceWarp>(cw, rd, lane);
         __syncwarp();
       }
-    }
+    barMain<NTM>();
     // One loop over both sweeps so that the frame's forward code exists once: steps 0 .. T-1 are the forward
     // sweep (frame = step), steps T .. 2T-1 the adjoint sweep (frame = 2T-1-step: recompute it from its
     // checkpoint, then its adjoint).
-    const int n_steps = a.want_grad ? 2 * T : T;
     for (int step = 0; step <= n_steps; step++) {
       const bool rec = step >= T;
       const int f = rec ? 2 * T - 1 - step : step;
       if (step == T) {
         // between the sweeps: terminal goals, then the adjoint's carried state
-        if (active) {
-          phaseTerminal(c, lane, loss);
-          __syncwarp();
-        }
+        if (active) phaseTerminal(c, slot, loss);
         if (!a.want_grad) break;
         c.r_out = nullptr;
-        c.emit = false;
         c.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
         if (active) {
-          bphaseInit(c, lane);
+          bphaseInit(c, slot);
           const double *ck = ckpt + (size_t)(T - 1) * CK;
 #pragma unroll
-          for (int i = 0; i < kPre; i++) pre[i] = (lane + 32 * i < CK) ? ck[lane + 32 * i] : 0.0;
-          __syncwarp();
+          for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
         }
+        barMain<NTM>();
       }
       if (step == n_steps) break;
 
       // ---- the frame, forward
-      if (active) {
-        if (!rec) {
-          PH(12, phaseBeginFrame(c, lane, f, ckpt + (size_t)f * CK); __syncwarp());
-        } else {
-          PH(13, phaseLoadCheckpoint(c, lane, pre); __syncwarp());
-          if (f > 0) {  // the next checkpoint lands while this frame is being worked on
-            const double *ck = ckpt + (size_t)(f - 1) * CK;
-#pragma unroll
-            for (int i = 0; i < kPre; i++) pre[i] = (lane + 32 * i < CK) ? ck[lane + 32 * i] : 0.0;
-          }
-        }
-        PH(0, phaseSim(c, lane); __syncwarp());
-        PH(1, for (int sl = 1; sl <= L; sl++) {
-          phaseChain(c, lane, sl);
-          __syncwarp();
-        });
-        PH(2, phaseObserve(c, lane, f, loss));
+      if (!rec) {
+        PH(12, if (active) phaseBeginFrame(c, slot, f, ckpt + (size_t)f * CK));
+      } else {
+        PH(13, if (active) phaseLoadCheckpoint(c, slot, pre));
       }
+      barAll();  // A: the body step may start
+      if (rec && active && f > 0) {  // the next checkpoint lands while this frame is being worked on
+        const double *ck = ckpt + (size_t)(f - 1) * CK;
+#pragma unroll
+        for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
+      }
+      PH(0, if (active) phaseSim(c, slot); barMain<NTM>());
+      PH(1, if (warp < live) for (int rd = 0; rd < n_round; rd++) {
+        fkRoundForward<1, DeviceWarp>(cw, rd, lane);
+        __syncwarp();
+      });
+      PH(15, barAll());  // B: link poses and the body step are complete
+      PH(2, if (active) { if (rec) phaseObserve<false>(c, slot, f, loss); else phaseObserve<true>(c, slot, f, loss); });
       if (n_layers) {
         // The policy layers' epilogues carry what follows them: activity / command regularisation rows and
         // tanh (dexenv_grasp.h:137-146,186-199), so the hidden and control steps cost no phase of their own.
         const long row_act = (long)f * rows_frame + H[H_ROW_ACT], row_cmd = (long)f * rows_frame + H[H_ROW_CMD];
-        PH(3, __syncthreads());
+        PH(3, barMain<NTM>());
         if (n_layers == 2) {
           PH(4, denseTiles(XS, a.s_X, sW1, a.s_W1, 1, k1, n_hid, warp, NW, lane, [=, &loss](int g, int j, double v) {
             v += sB1[j];
             HS[g * a.s_H + j] = v;
             AS[g * a.s_H + j] = tanh(v);
             if (!rec && j < n_hid && g < live) {
-              const double r = v * w_reg;
-              loss += r * r;
-              if (grp_r) grp_r[(row_act + j) * a.R + g] = r;
+              const double rr = v * w_reg;
+              loss += rr * rr;
+              if (grp_r) grp_r[(row_act + j) * a.R + g] = rr;
             }
           }));
-          PH(3, __syncthreads());
+          PH(3, barMain<NTM>());
         }
         {
           const double *Xl = n_layers == 2 ? AS : XS, *Wl = n_layers == 2 ? sW2 : sW1, *Bl = n_layers == 2 ? sB2 : sB1;
@@ -311,181 +492,83 @@ __global__ void __launch_bounds__(NW * 32, 1)
                              OS[g * a.s_O + j] = v;
                              if (j < nq && g < NW) vel[g * region + j] = tanh(v);
                              if (!rec && j < n_out && g < live) {
-                               const double r = v * w_creg;
-                               loss += r * r;
-                               if (grp_r) grp_r[(row_cmd + j) * a.R + g] = r;
+                               const double rr = v * w_creg;
+                               loss += rr * rr;
+                               if (grp_r) grp_r[(row_cmd + j) * a.R + g] = rr;
                              }
                            }));
         }
-        PH(3, __syncthreads());
-        if (active) {
-          PH(8, phaseContact1(c, lane, f, loss); __syncwarp());
-          PH(9, phaseContact2(c, lane, f); __syncwarp());
-          if (!rec) {
-            PH(10, phaseContact3(c, lane, f, loss); __syncwarp());
-          }
+        PH(3, barMain<NTM>());
+        PH(8, if (active) { if (rec) phaseContact1<false>(c, slot, f, loss); else phaseContact1<true>(c, slot, f, loss); } barMain<NTM>());
+        PH(9, if (active) phaseContact2(c, slot, f); barMain<NTM>());
+        if (!rec) {
+          PH(10, if (active) phaseContact3(c, slot, f, loss); barMain<NTM>());
         }
       }
       if (!rec) continue;
 
       // ---- the frame, adjoint
-      if (active) {
-        PH(32, bphaseBegin(c, lane, f); __syncwarp(); if (f == T - 1 || f == 0) {
-          bphaseBegin2(c, lane, f);
-          __syncwarp();
-        });
-        if (n_layers) {
-          PH(33, bphaseContact3(c, lane, f); __syncwarp());
-          PH(34, bphaseContact2(c, lane, f); __syncwarp());
-          PH(35, bphaseContact1(c, lane, f); __syncwarp());
-          PH(36, bphaseControl(c, lane, f));
-        }
-      }
+      PH(32, if (active) bphaseBegin(c, slot, f); barMain<NTM>(); if (f == T - 1 || f == 0) {
+        if (active) bphaseBegin2(c, slot, f);
+        barMain<NTM>();
+      });
       if (n_layers) {
-        PH(37, __syncthreads());
-        // adjoint of the last layer: input adjoint (with the tanh / activity-row adjoint of the hidden layer in
-        // its epilogue), then dW (register tiles) and db
-        if (n_layers == 2) {
-          const long row_act = (long)f * rows_frame + H[H_ROW_ACT];
-          PH(38, denseTiles(GOS, a.s_O, sW2, 1, a.s_W2, (n_out + 3) & ~3, n_hid, warp, NW, lane,
-                            [=](int g, int i, double v) {
-                              const bool on = g < live && i < n_hid;
-                              const double av = AS[g * a.s_H + i];
-                              const double sd = grp_seed ? (on ? grp_seed[(row_act + i) * a.R + g] : 0.0)
-                                                         : HS[g * a.s_H + i] * w_reg;
-                              GHS[g * a.s_H + i] = on ? v * (1.0 - av * av) + sd * w_reg : 0.0;
-                            }));
-        } else {
-          PH(38, denseTiles(GOS, a.s_O, sW1, 1, a.s_W1, (n_out + 3) & ~3, n_in, warp, NW, lane,
-                            [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
-        }
-#ifdef TRX_ROLLOUT_PROFILE
-        long long _tw = clock64();
-#endif
-        if (MAXT > 0) {
-          // dW += X^T GY, K = the 8 rollouts = two DMMAs per 8x8 tile; the first DMMA of every tile, then the second,
-          // so that consecutive DMMAs never wait on each other's accumulator.  With two layers the first
-          // layer's tiles wait for its output adjoint (below).
-          const int sx = n_layers == 2 ? a.s_H : a.s_X;
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-#pragma unroll
-            for (int u = 0; u < MAXT; u++) {
-              const int tl = warp + u * NW;
-              if (tl < a.n_tiles && (n_layers == 1 || tl >= a.tiles_1)) {
-                const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
-                dmma884(acc[u][0], acc[u][1], xa[(t4 + 4 * half) * sx], yb[(t4 + 4 * half) * a.s_O]);
-              }
-            }
-          }
-        }
-        {
-          // db of the last layer: element e of {b1, b2} lives in thread e (mod nt)
-          const int base = n_layers == 2 ? n_hid : 0;
-          for (int e = tid, slot = 0; e < base + n_out; e += nt, slot++) {
-            if (e < base) continue;
-            const double *gy = GOS + (e - base);
-            double sgy = 0;
-            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_O];
-            if (slot == 0) gb0 += sgy;
-            else gb1 += sgy;
-          }
-        }
-#ifdef TRX_ROLLOUT_PROFILE
-        if (tid == 0) sprof[39] += clock64() - _tw;
-#endif
-        PH(37, __syncthreads());
-        if (n_layers == 2) {
-          PH(41, denseTiles(GHS, a.s_H, sW1, 1, a.s_W1, k2, n_in, warp, NW, lane,
-                            [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
-#ifdef TRX_ROLLOUT_PROFILE
-          _tw = clock64();
-#endif
-          if (MAXT > 0) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-#pragma unroll
-              for (int u = 0; u < MAXT; u++) {
-                const int tl = warp + u * NW;
-                if (tl < a.tiles_1) {
-                  const double *xa = sm + tile_tab[2 * tl] + gi, *yb = sm + tile_tab[2 * tl + 1] + gi;
-                  dmma884(acc[u][0], acc[u][1], xa[(t4 + 4 * half) * a.s_X], yb[(t4 + 4 * half) * a.s_H]);
-                }
-              }
-            }
-          }
-          for (int e = tid, slot = 0; e < n_hid; e += nt, slot++) {
-            const double *gy = GHS + e;
-            double sgy = 0;
-            for (int g = 0; g < 8; g++) sgy += gy[g * a.s_H];
-            if (slot == 0) gb0 += sgy;
-            else gb1 += sgy;
-          }
-#ifdef TRX_ROLLOUT_PROFILE
-          if (tid == 0) sprof[42] += clock64() - _tw;
-#endif
-          PH(37, __syncthreads());
-        }
+        PH(33, if (active) bphaseContact3(c, slot, f); barMain<NTM>());
+        PH(34, if (active) bphaseContact2(c, slot, f); barMain<NTM>());
+        PH(35, if (active) bphaseContact1(c, slot, f); barMain<NTM>());
+        PH(36, if (active) bphaseControl(c, slot, f));
       }
-      if (active) {
-        PH(43, bphaseObserve(c, lane, f); __syncwarp());
-        PH(44, for (int sl = L; sl >= 1; sl--) {
-          bphaseChain(c, lane, sl);
+      PH(46, barAll());  // C: the helper warps take dW and db of the last layer from here
+      if (n_layers == 2) {
+        // input adjoint of the last layer, with the tanh / activity-row adjoint of the hidden layer in its epilogue
+        const long row_act = (long)f * rows_frame + H[H_ROW_ACT];
+        PH(38, denseTiles(GOS, a.s_O, sW2, 1, a.s_W2, (n_out + 3) & ~3, n_hid, warp, NW, lane,
+                          [=](int g, int i, double v) {
+                            const bool on = g < live && i < n_hid;
+                            const double av = AS[g * a.s_H + i];
+                            const double sd = grp_seed ? (on ? grp_seed[(row_act + i) * a.R + g] : 0.0)
+                                                       : HS[g * a.s_H + i] * w_reg;
+                            GHS[g * a.s_H + i] = on ? v * (1.0 - av * av) + sd * w_reg : 0.0;
+                          }));
+      } else if (n_layers == 1) {
+        PH(38, denseTiles(GOS, a.s_O, sW1, 1, a.s_W1, (n_out + 3) & ~3, n_in, warp, NW, lane,
+                          [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
+      }
+      PH(47, barAll());  // D: ... and of the first layer from here
+      if (n_layers == 2) {
+        PH(41, denseTiles(GHS, a.s_H, sW1, 1, a.s_W1, k2, n_in, warp, NW, lane,
+                          [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
+        PH(37, barMain<NTM>());
+      }
+      PH(43, if (active) bphaseObserve(c, slot, f); barMain<NTM>(); if (warp < live) bphaseObjectGather(cw, lane));
+      PH(48, barAll());  // E: the body adjoint may start
+      PH(44, if (warp < live) {
+        for (int rd = n_round - 1; rd >= 0; rd--) {
+          fkRoundReverse<1, DeviceWarp>(cw, rd, lane);
           __syncwarp();
-        });
-        PH(45, bphaseSim(c, lane); __syncwarp());
-      }
+        }
+        fkClearStatics(cw, lane);
+        bphaseSim(cw, lane);
+      });
+      PH(49, barAll());  // G
     }
   }
 
 #ifdef TRX_ROLLOUT_PROFILE
-  __syncthreads();
+  barMain<NTM>();
   if (blockIdx.x == 0 && tid < 64) g_rollout_prof[tid] = sprof[tid];
 #endif
-  // ---- this CTA's partial loss and gradient
-  double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
+  // ---- this CTA's partial loss
   {
     for (int off = 16; off > 0; off >>= 1) loss += __shfl_down_sync(0xffffffffu, loss, off);
     double *red = sm + a.o_red;
-    __syncthreads();
+    barMain<NTM>();
     if (lane == 0) red[warp] = loss;
-    __syncthreads();
+    barMain<NTM>();
     if (tid == 0) {
-      double s = 0;
-      for (int w = 0; w < NW; w++) s += red[w];
-      part[0] = a.accumulate ? part[0] + s : s;
-    }
-  }
-  if (a.want_grad && n_layers) {
-    const int gi = lane >> 2, t4 = lane & 3;
-    if (MAXT > 0) {
-#pragma unroll
-      for (int u = 0; u < MAXT; u++) {
-        const int tl = warp + u * NW;
-        if (tl >= a.n_tiles) continue;
-        int ti, tj, base, width, rows;
-        if (tl < a.tiles_1) {
-          ti = tl / a.tiles_j1, tj = tl - ti * a.tiles_j1;
-          base = H[H_W1], width = n1, rows = n_in;
-        } else {
-          const int tiles_j2 = (n_out + 7) >> 3;
-          ti = (tl - a.tiles_1) / tiles_j2, tj = (tl - a.tiles_1) - ti * tiles_j2;
-          base = H[H_W2], width = n_out, rows = n_hid;
-        }
-        const int i = ti * 8 + gi, j = tj * 8 + 2 * t4;
-        if (i < rows) {
-          double *p = part + 1 + base + i * width + j;
-          if (j < width) p[0] = a.accumulate ? p[0] + acc[u][0] : acc[u][0];
-          if (j + 1 < width) p[1] = a.accumulate ? p[1] + acc[u][1] : acc[u][1];
-        }
-      }
-    }
-    const int nb = (n_layers == 2 ? n_hid : 0) + n_out;
-    for (int e = tid, slot = 0; e < nb; e += nt, slot++) {
-      const double v = slot == 0 ? gb0 : gb1;
-      // {b1, b2} order; with one layer the only bias is b1
-      const int idx = n_layers == 2 ? (e < n_hid ? H[H_B1] + e : H[H_B2] + (e - n_hid)) : H[H_B1] + e;
-      part[1 + idx] = a.accumulate ? part[1 + idx] + v : v;
+      double sum = 0;
+      for (int w = 0; w < NW; w++) sum += red[w];
+      part[0] = a.accumulate ? part[0] + sum : sum;
     }
   }
 }
@@ -532,7 +615,7 @@ struct trx_rollout {
   KHeader hdr;
   KArgs args;
   int device = 0;
-  int nw = 8, maxt = 0, grid = 0;
+  int nw = 8, u1 = 0, ul = 0, grid = 0;
   size_t smem_bytes = 0;
   uint64_t lanes = 0, chunk = 0, n_chunks = 0;
   bool scalar_rows = true;
@@ -546,11 +629,14 @@ namespace {
 
 typedef void (*KernelFn)(const KHeader, const KArgs);
 struct Variant {
-  int nw, maxt;
+  int nw, u1, ul;  // rollouts per CTA, dW tiles per warp of the first / last layer
   KernelFn fn;
 };
-#define RL_VARIANT(NW, MAXT) {NW, MAXT, trx_rollout_kernel<NW, MAXT>}
-const Variant kVariants[] = {RL_VARIANT(8, 8), RL_VARIANT(8, 18), RL_VARIANT(8, 28), RL_VARIANT(4, 28)};
+#define RL_VARIANT(NW, U1, UL) {NW, U1, UL, trx_rollout_kernel<NW, U1, UL>}
+// smallest first: (2, 7) one-layer and narrow policies, (7, 13) the 41 -> 64 -> 83 policy of the benchmark (20 tiles
+// = 80 of the 128 registers a thread of a 16-warp CTA can have), 4 rollouts per CTA when 8 regions do not fit the
+// shared memory.  Wider policies have no re-rolled form here (TRX_ERR_UNSUPPORTED: use the tape objective).
+const Variant kVariants[] = {RL_VARIANT(8, 2, 7), RL_VARIANT(8, 7, 13), RL_VARIANT(4, 7, 13)};
 
 #define RL_CUDA(expr)                                                                  \
   do {                                                                                 \
@@ -614,8 +700,9 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   a.nx = I[H_NX];
   a.frames = ro->plan.frames;
   a.tiles_j1 = (n1 + 7) / 8;
-  a.tiles_1 = ((n_in + 7) / 8) * a.tiles_j1;
-  a.n_tiles = a.tiles_1 + (n_layers == 2 ? ((n_hid + 7) / 8) * ((n_out + 7) / 8) : 0);
+  a.tiles_1 = n_layers == 2 ? ((n_in + 7) / 8) * a.tiles_j1 : 0;
+  a.tiles_jl = (n_out + 7) / 8;
+  a.tiles_l = ((n_layers == 2 ? n_hid : n_in) + 7) / 8 * a.tiles_jl;
   const Variant *pick = nullptr;
   for (const Variant &v : kVariants) {
     int off = 0;
@@ -644,14 +731,15 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
     a.o_GX = take(8 * a.s_X);
     a.o_GH = take(8 * a.s_H);
     a.o_GO = take(8 * a.s_O);
-    a.o_tile = take(a.n_tiles);
+    a.o_tile = take(kHelperWarps * (v.u1 + v.ul));
+    a.o_zero = take(8 * std::max(a.s_O, std::max(a.s_X, a.s_H)) + 8);
     a.o_red = take(8);
     a.o_region = off;
     off += v.nw * I[H_REGION];
     size_t bytes = (size_t)off * sizeof(double);
-    if ((a.n_tiles + v.nw - 1) / v.nw > v.maxt) continue;
+    if ((a.tiles_1 + kDwWarps - 1) / kDwWarps > v.u1 || (a.tiles_l + kDwWarps - 1) / kDwWarps > v.ul) continue;
     if (bytes > (size_t)prop.sharedMemPerBlockOptin) continue;
-    if ((n_layers == 2 ? n_hid : 0) + n_out > 2 * v.nw * 32) continue;  // bias gradients: two per thread
+    if ((n_layers == 2 ? n_hid : 0) + n_out > 2 * kDwWarps * 32) continue;  // bias gradients: two per dW thread
     pick = &v;
     ro->smem_bytes = bytes;
     break;
@@ -661,7 +749,8 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
     return TRX_ERR_UNSUPPORTED;
   }
   ro->nw = pick->nw;
-  ro->maxt = pick->maxt;
+  ro->u1 = pick->u1;
+  ro->ul = pick->ul;
   RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
 
   // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
@@ -720,7 +809,7 @@ uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key) {
   if (k == "rollouts_per_cta") return ro->nw;
   if (k == "grid") return ro->grid;
   if (k == "shared_bytes") return ro->smem_bytes;
-  if (k == "tiles_per_warp") return ro->maxt;
+  if (k == "tiles_per_warp") return ro->u1 + ro->ul;
   if (k == "n_joints") return I[H_NJ];
   if (k == "n_levels") return I[H_NSUPER];
   if (k == "n_controlled") return I[H_NQ];
@@ -751,7 +840,7 @@ trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out,
   RL_CUDA(cudaSetDevice(ro->device));
   KernelFn fn = nullptr;
   for (const Variant &v : kVariants)
-    if (v.nw == ro->nw && v.maxt == ro->maxt) fn = v.fn;
+    if (v.nw == ro->nw && v.u1 == ro->u1 && v.ul == ro->ul) fn = v.fn;
   KArgs a = ro->args;
   a.x = d_x;
   a.r_out = d_r;
@@ -763,7 +852,7 @@ trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out,
     a.n_groups = (int)((a.count + ro->nw - 1) / ro->nw);
     a.accumulate = ch > 0 ? 1 : 0;
     // every CTA of the grid writes its partial slot, also when it has no group in this chunk
-    fn<<<ro->grid, ro->nw * 32, ro->smem_bytes, stream>>>(ro->hdr, a);
+    fn<<<ro->grid, (ro->nw + kHelperWarps) * 32, ro->smem_bytes, stream>>>(ro->hdr, a);
     ro->launches++;
   }
   const int nx = ro->args.nx;
@@ -784,7 +873,7 @@ extern "C" void trx_rollout_profile_dump() {
   const char *names[64] = {};
   names[0] = "sim", names[1] = "chain", names[2] = "observe", names[3] = "barriers(fwd)", names[4] = "dense1", names[5] = "hidden";
   names[6] = "dense2", names[7] = "control", names[8] = "contact1", names[9] = "contact2", names[10] = "contact3";
-  names[11] = "contactsum", names[12] = "beginframe+ckpt", names[13] = "loadckpt";
+  names[15] = "barrier B (body)", names[50] = "dW warp: last layer", names[51] = "dW warp: first layer", names[46] = "barrier C", names[47] = "barrier D (dW last)", names[48] = "barrier E (dW first)", names[49] = "barrier G (body adj)", names[11] = "contactsum", names[12] = "beginframe+ckpt", names[13] = "loadckpt";
   names[32] = "b.begin", names[33] = "b.contact3", names[34] = "b.contact2", names[35] = "b.contact1", names[36] = "b.control";
   names[37] = "b.barriers", names[38] = "b.dense2 gx", names[39] = "b.dW2+db2", names[40] = "b.hidden", names[41] = "b.dense1 gx";
   names[42] = "b.dW1+db1", names[43] = "b.observe", names[44] = "b.chain", names[45] = "b.sim";
@@ -792,8 +881,8 @@ extern "C" void trx_rollout_profile_dump() {
   for (int i = 0; i < 64; i++) total += h[i];
   for (int i = 0; i < 64; i++) {
     if (!h[i]) continue;
-    const char *n = i >= 16 && i < 32 ? names[i - 16] : names[i];
-    std::printf("%-2d %s%-18s %12lld cycles %5.1f%%\n", i, i >= 16 && i < 32 ? "re." : "", n ? n : "?", h[i], 100.0 * h[i] / total);
+    const char *n = names[i];
+    std::printf("%-2d %-22s %12lld cycles %5.1f%%\n", i, n ? n : "?", h[i], 100.0 * h[i] / total);
   }
 }
 #endif

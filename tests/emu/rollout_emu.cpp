@@ -56,6 +56,16 @@ void denseReverse(const double *x, const double *gy, const double *W, int n_in, 
 
 #define LANES(stmt) for (int lane = 0; lane < 32; lane++) { stmt; }
 
+// lane exchange of the warp-scan phases on 32-element arrays (the device uses warp shuffles)
+struct HostWarp {
+  template <class T> static void up(const T (&x)[32], int d, T (&o)[32]) {
+    for (int i = 0; i < 32; i++) o[i] = i >= d ? x[i - d] : x[i];
+  }
+  template <class T> static void down(const T (&x)[32], int d, T (&o)[32]) {
+    for (int i = 0; i < 32; i++) o[i] = i + d < 32 ? x[i + d] : x[i];
+  }
+};
+
 extern "C" {
 
 const char *rollout_emu_last_error() { return g_error.c_str(); }
@@ -119,13 +129,20 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
       c.seed = nullptr;
       c.r_stride = lanes;
       c.frames = T;
-      c.emit = true;
       double lane_loss[32] = {0};
       double pr[3] = {params[0 * lanes + g0], params[1 * lanes + g0], params[2 * lanes + g0]};
+      auto forwardKinematics = [&](const Ctx &cc) {
+        for (int rd = 0; rd < I[H_NROUND]; rd++) fkRoundForward<32, HostWarp>(cc, rd, 0);
+      };
       auto forwardFrame = [&](int f, const Ctx &cc, double *ll, bool store) {
         LANES(phaseSim(cc, lane));
-        for (int lv = 1; lv <= L; lv++) LANES(phaseChain(cc, lane, lv));
-        LANES(phaseObserve(cc, lane, f, ll[lane]));
+        phaseBody(cc);
+        forwardKinematics(cc);
+        if (store) {
+          LANES(phaseObserve<true>(cc, lane, f, ll[lane]));
+        } else {
+          LANES(phaseObserve<false>(cc, lane, f, ll[lane]));
+        }
         if (n_layers == 2) {
           denseForward(cc.x, W1, b1, n_in, n_hid, cc.h);
           LANES(phaseHidden(cc, lane, f, ll[lane]));
@@ -135,7 +152,11 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
         }
         if (n_layers) {
           LANES(phaseControl(cc, lane, f, ll[lane]));
-          LANES(phaseContact1(cc, lane, f, ll[lane]));
+          if (store) {
+            LANES(phaseContact1<true>(cc, lane, f, ll[lane]));
+          } else {
+            LANES(phaseContact1<false>(cc, lane, f, ll[lane]));
+          }
           LANES(phaseContact2(cc, lane, f));
           if (store) {
             LANES(phaseContact3(cc, lane, f, ll[lane]));
@@ -143,7 +164,7 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
         }
       };
       LANES(phaseInit(c, lane, pr));
-      for (int lv = 1; lv <= L; lv++) LANES(phaseChain(c, lane, lv));
+      forwardKinematics(c);
       for (int f = 0; f < T; f++) {
         LANES(phaseBeginFrame(c, lane, f, &ckpt[(size_t)f * I[H_CKPT]]));
         forwardFrame(f, c, lane_loss, true);
@@ -154,9 +175,8 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
       // ---- adjoint sweep
       Ctx cb = c;
       cb.r_out = nullptr;
-      cb.emit = false;
       cb.seed = seed_wide ? seed_wide + n_scalar + g0 : nullptr;
-      double dummy[32];
+      double dummy[32] = {0};
       LANES(bphaseInit(cb, lane));
       for (int f = T - 1; f >= 0; f--) {
         const double *ck = &ckpt[(size_t)f * I[H_CKPT]];
@@ -182,8 +202,11 @@ int rollout_emu_eval(const char *options, int lanes, const double *params, const
           }
         }
         LANES(bphaseObserve(cb, lane, f));
-        for (int lv = L; lv >= 1; lv--) LANES(bphaseChain(cb, lane, lv));
+        LANES(bphaseObjectGather(cb, lane));
+        for (int rd = I[H_NROUND] - 1; rd >= 0; rd--) fkRoundReverse<32, HostWarp>(cb, rd, 0);
+        LANES(fkClearStatics(cb, lane));
         LANES(bphaseSim(cb, lane));
+        bphaseBody(cb);
       }
     }
     *loss_out = loss_total;
