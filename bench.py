@@ -155,9 +155,8 @@ def workload_config(n_gpus):
     }
     if ENGINE == "rollout":
         cfg["engine"] = "re-rolled rollout objective (one frame program + carried state; hand-written forward/adjoint kernels)"
-        cfg["l2"] = ("every evaluation rewrites its per-frame state checkpoints (%.0f MB per GPU, larger than the "
-                     "126 MB L2) before the adjoint reads them back in reverse order; no flush needed" % (
-                         FRAMES * lanes * 960 / 1e6))
+        cfg["l2"] = ("every evaluation rewrites its per-frame checkpoints (several hundred MB per GPU, see device_bytes; "
+                     "larger than the 126 MB L2) before the adjoint reads them back in reverse order; no flush needed")
     else:
         cfg["engine"] = "interpreted flat tape"
         cfg["dense_layers"] = "one block instruction per layer (x_dense)" if FUSE_DENSE else "reference expansion (batch + dot4add per weight)"
@@ -377,7 +376,7 @@ def main():
     if ENGINE == "rollout":
         launch_ms = kernel_ms / n_chunks
         alg_bytes = b_alg  # one launch does both sweeps
-        kernel_name = "trx_rollout_kernel<8,18> (forward sweep + adjoint sweep, one launch per evaluation)"
+        kernel_name = "trx_rollout_kernel<8,7,13> (forward sweep + adjoint sweep, one launch per evaluation)"
     else:
         launch_ms = tape_ms[2] / (args.steps * n_chunks)
         alg_bytes = b_alg / 2  # the adjoint launch must read the per-frame state once

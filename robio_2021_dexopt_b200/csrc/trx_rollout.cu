@@ -57,6 +57,7 @@ struct KArgs {
   long count;        // rollouts of this launch
   int ni, nd, nx;
   int frames, n_groups, want_grad, accumulate;
+  int ckpt_doubles;  // doubles per (rollout, frame) checkpoint
   // shared-memory layout, in doubles
   int o_D, o_I, o_W1, o_B1, o_W2, o_B2, s_W1, s_W2, r_W1, r_W2;
   int o_X, o_H, o_A, o_O, o_GX, o_GH, o_GO, s_X, s_H, s_O;
@@ -152,6 +153,12 @@ template <int NTHREADS> __device__ __forceinline__ void barMain() {
   asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS)
+__device__ __forceinline__ void cpAsync8(double *dst_shared, const double *src_global) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global)
+               : "memory");
+}
+
 constexpr int kHelperWarps = 8;            // helper warps of a CTA:
 constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one body warp
 
@@ -222,7 +229,11 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
   const double *sW1 = sm + a.o_W1, *sB1 = sm + a.o_B1, *sW2 = sm + a.o_W2, *sB2 = sm + a.o_B2;
   double *XS = sm + a.o_X, *HS = sm + a.o_H, *AS = sm + a.o_A, *OS = sm + a.o_O;
   double *GXS = sm + a.o_GX, *GHS = sm + a.o_GH, *GOS = sm + a.o_GO;
+  // a frame's checkpoint: the carried state (H_CKPT doubles), then what the policy layers produced in the frame --
+  // hidden pre-activations, activations, outputs, tanh of the joint commands -- so that the adjoint sweep recomputes
+  // kinematics and contacts only
   const int T = a.frames, CK = H[H_CKPT];
+  const int CKX = a.ckpt_doubles;  // stride
   const int n_steps = a.want_grad ? 2 * T : T;
   double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
 
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
     const long local = grp_first + r;
     const bool active = r < live;
     const long rollout = a.first + local;
-    double *ckpt = a.ckpt + (size_t)local * T * CK;
+    double *ckpt = a.ckpt + (size_t)local * T * CKX;
     // element (row, g) of the group's residual rows / seeds at [row * R + g]
     double *grp_r = a.r_out ? a.r_out + H[H_NSCALAR] + a.first + grp_first : nullptr;
     const double *grp_seed = a.seed ? a.seed + H[H_NSCALAR] + a.first + grp_first : nullptr;
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         c.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
         if (active) {
           bphaseInit(c, slot);
-          const double *ck = ckpt + (size_t)(T - 1) * CK;
+          const double *ck = ckpt + (size_t)(T - 1) * CKX;
 #pragma unroll
           for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
         }
@@ -446,13 +457,25 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
 
       // ---- the frame, forward
       if (!rec) {
-        PH(12, if (active) phaseBeginFrame(c, slot, f, ckpt + (size_t)f * CK));
+        PH(12, if (active) phaseBeginFrame(c, slot, f, ckpt + (size_t)f * CKX));
       } else {
-        PH(13, if (active) phaseLoadCheckpoint(c, slot, pre));
+        PH(13, if (active) {
+          phaseLoadCheckpoint(c, slot, pre);
+          // the frame's policy values travel from the checkpoint straight into the activation matrices while
+          // the kinematics are recomputed (nobody reads them before the contact phases)
+          const double *ck = ckpt + (size_t)f * CKX + CK;
+          for (int e = slot; e < n_hid; e += 32) {
+            cpAsync8(c.h + e, ck + e);
+            cpAsync8(c.a + e, ck + n_hid + e);
+          }
+          for (int e = slot; e < n_out; e += 32) cpAsync8(c.out + e, ck + 2 * n_hid + e);
+          for (int e = slot; e < nq; e += 32) cpAsync8(c.s + H[R_VEL] + e, ck + 2 * n_hid + n_out + e);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        });
       }
       barAll();  // A: the body step may start
       if (rec && active && f > 0) {  // the next checkpoint lands while this frame is being worked on
-        const double *ck = ckpt + (size_t)(f - 1) * CK;
+        const double *ck = ckpt + (size_t)(f - 1) * CKX;
 #pragma unroll
         for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
       }
@@ -467,13 +490,14 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         // The policy layers' epilogues carry what follows them: activity / command regularisation rows and
         // tanh (dexenv_grasp.h:137-146,186-199), so the hidden and control steps cost no phase of their own.
         const long row_act = (long)f * rows_frame + H[H_ROW_ACT], row_cmd = (long)f * rows_frame + H[H_ROW_CMD];
+        if (rec) asm volatile("cp.async.wait_group 0;" ::: "memory");
         PH(3, barMain<NTM>());
-        if (n_layers == 2) {
+        if (!rec && n_layers == 2) {
           PH(4, denseTiles(XS, a.s_X, sW1, a.s_W1, 1, k1, n_hid, warp, NW, lane, [=, &loss](int g, int j, double v) {
             v += sB1[j];
             HS[g * a.s_H + j] = v;
             AS[g * a.s_H + j] = tanh(v);
-            if (!rec && j < n_hid && g < live) {
+            if (j < n_hid && g < live) {
               const double rr = v * w_reg;
               loss += rr * rr;
               if (grp_r) grp_r[(row_act + j) * a.R + g] = rr;
@@ -481,7 +505,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
           }));
           PH(3, barMain<NTM>());
         }
-        {
+        if (!rec) {
           const double *Xl = n_layers == 2 ? AS : XS, *Wl = n_layers == 2 ? sW2 : sW1, *Bl = n_layers == 2 ? sB2 : sB1;
           const int sXl = n_layers == 2 ? a.s_H : a.s_X, sWl = n_layers == 2 ? a.s_W2 : a.s_W1;
           double *vel = sm + a.o_region + H[R_VEL];
@@ -491,14 +515,20 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
                              v += Bl[j];
                              OS[g * a.s_O + j] = v;
                              if (j < nq && g < NW) vel[g * region + j] = tanh(v);
-                             if (!rec && j < n_out && g < live) {
+                             if (j < n_out && g < live) {
                                const double rr = v * w_creg;
                                loss += rr * rr;
                                if (grp_r) grp_r[(row_cmd + j) * a.R + g] = rr;
                              }
                            }));
+          PH(3, barMain<NTM>());
+          if (active) {
+            double *ck = ckpt + (size_t)f * CKX + CK;
+            for (int e = slot; e < n_hid; e += 32) ck[e] = c.h[e], ck[n_hid + e] = c.a[e];
+            for (int e = slot; e < n_out; e += 32) ck[2 * n_hid + e] = c.out[e];
+            for (int e = slot; e < nq; e += 32) ck[2 * n_hid + n_out + e] = c.s[H[R_VEL] + e];
+          }
         }
-        PH(3, barMain<NTM>());
         PH(8, if (active) { if (rec) phaseContact1<false>(c, slot, f, loss); else phaseContact1<true>(c, slot, f, loss); } barMain<NTM>());
         PH(9, if (active) phaseContact2(c, slot, f); barMain<NTM>());
         if (!rec) {
@@ -754,7 +784,9 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
 
   // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
-  const uint64_t ck_bytes_per_rollout = (uint64_t)a.frames * I[H_CKPT] * sizeof(double);
+  a.ckpt_doubles = I[H_CKPT] + 2 * n_hid + n_out + I[H_NQ];
+  a.ckpt_doubles += a.ckpt_doubles & 1;  // 16-byte rows
+  const uint64_t ck_bytes_per_rollout = (uint64_t)a.frames * a.ckpt_doubles * sizeof(double);
   uint64_t chunk = lanes;
   if (max_device_bytes && chunk * ck_bytes_per_rollout > max_device_bytes)
     chunk = std::max<uint64_t>(ro->nw, max_device_bytes / ck_bytes_per_rollout / ro->nw * ro->nw);
@@ -799,13 +831,14 @@ uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key) {
   if (k == "chunk_lanes") return ro->chunk;
   if (k == "n_chunks") return ro->n_chunks;
   if (k == "device_bytes")
-    return (uint64_t)((ro->chunk + ro->nw - 1) / ro->nw * ro->nw) * ro->plan.frames * I[H_CKPT] * 8 +
+    return (uint64_t)((ro->chunk + ro->nw - 1) / ro->nw * ro->nw) * ro->plan.frames * ro->args.ckpt_doubles * 8 +
            (uint64_t)ro->grid * (1 + I[H_NX]) * 8 + 3 * ro->lanes * 8;
   if (k == "launches_per_evaluation") return ro->n_chunks + 1;
   if (k == "residual_elems") return (uint64_t)I[H_NSCALAR] + ((uint64_t)ro->plan.frames * I[H_ROWS_FRAME] + 6) * ro->lanes;
   if (k == "n_scalar_rows") return I[H_NSCALAR];
   if (k == "rows_per_frame") return I[H_ROWS_FRAME];
-  if (k == "checkpoint_bytes_per_unit") return (uint64_t)I[H_CKPT] * 8;
+  if (k == "checkpoint_bytes_per_unit") return (uint64_t)ro->args.ckpt_doubles * 8;
+  if (k == "carried_state_bytes_per_unit") return (uint64_t)I[H_CKPT] * 8;
   if (k == "rollouts_per_cta") return ro->nw;
   if (k == "grid") return ro->grid;
   if (k == "shared_bytes") return ro->smem_bytes;

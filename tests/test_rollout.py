@@ -168,8 +168,9 @@ def test_rollout_full_size_properties(cuda_engine):
     l_b, g_b = full.evaluate(x)
     assert l_a == l_b and np.array_equal(g_a, g_b)
     assert np.isfinite(l_a) and np.all(np.isfinite(g_a))
-    # device memory does not depend on anything but rollouts x frames x checkpoint
-    assert full.info("device_bytes") < 400e6
+    # device memory is rollouts x frames x checkpoint (carried state + the frame's policy values), nothing else
+    assert full.info("device_bytes") < 1024 * 256 * full.info("checkpoint_bytes_per_unit") + 20e6
+    assert full.info("checkpoint_bytes_per_unit") <= 8 * (120 + 2 * 64 + 83 + 29 + 1)
     half0 = _objective(cuda_engine, opts, lanes // 2)
     half1 = _objective(cuda_engine, opts, lanes // 2, scalar_rows=False)
     half0.parameterize(pw[:, :lanes // 2].copy())
