@@ -150,7 +150,8 @@ def workload_config(n_gpus):
                     "effectors, floating object), policy MLP 41->%d->83, horizon %d, %d rollouts per GPU" % (
                         " sharded as configs[3]" if n_gpus > 1 else "", HIDDEN, FRAMES, lanes),
         "frames": FRAMES, "rollouts_per_gpu": lanes, "rollouts": lanes * n_gpus,
-        "parallelism": "rollouts sharded over %d GPU(s); all-reduce of {loss, gradient} per step" % n_gpus if n_gpus > 1
+        "parallelism": "rollouts sharded over %d GPU(s); one NCCL all-reduce of {loss, gradient} per step, issued by the "
+                       "library on the evaluation's stream" % n_gpus if n_gpus > 1
         else "single GPU",
     }
     if ENGINE == "rollout":
@@ -293,21 +294,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:
+        # rollouts sharded over the ranks: the library sums {loss, gradient} over them (one ncclAllReduce on the
+        # evaluation's stream, include/trx_b200.h trx_objective_set_comm); torch.distributed only carries the id
+        from robio_2021_dexopt_b200.distributed import Communicator
+        comm = Communicator.from_torch_distributed(local_rank)
+        obj.set_comm(comm)
+
     def step_device():
         obj.evaluate_device(d_x.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(d_out)
 
     def step_e2e():
-        if world == 1:
-            # the reference-facing C-ABI call with host buffers (trx_objective_evaluate)
-            return obj.evaluate(x_host)
-        d_x.copy_(h_x, non_blocking=True)
-        obj.evaluate_device(d_x.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
-        dist.all_reduce(d_out)
-        h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(h_out[0]), h_out[1:].numpy()
+        # the reference-facing C-ABI call with host buffers (trx_objective_evaluate); with several ranks it ends
+        # with the all-reduce, so every rank returns the job's loss and gradient
+        return obj.evaluate(x_host)
 
     # ---- device-resident arm: warm-up, then exactly K timed steps
     for _ in range(args.warmup):
@@ -329,6 +329,8 @@ def main():
     # ---- the engine's launches alone (no all-reduce): CUDA events on the launching stream
     kernel_ms = None
     tape_ms = None
+    if world > 1:
+        obj.set_comm(None)
     if ENGINE == "rollout":
         k0 = torch.cuda.Event(enable_timing=True)
         k1 = torch.cuda.Event(enable_timing=True)
@@ -345,6 +347,8 @@ def main():
             tape_ms, _n = obj.profile_collect()
         obj.set_profiling(False)
 
+    if world > 1:
+        obj.set_comm(comm)
     # ---- end-to-end arm: host buffers in, host (loss, gradient) out, every step
     for _ in range(min(args.warmup, 2)):
         step_e2e()

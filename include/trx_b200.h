@@ -232,6 +232,27 @@ trx_status trx_objective_last_times(const trx_objective *o, float *ms3);
 trx_status trx_objective_set_profiling(trx_objective *o, int enable);
 trx_status trx_objective_profile_collect(trx_objective *o, double *ms3, uint64_t *evaluations);
 
+/* ---- multi-GPU: rollouts sharded over the ranks of one job ---------------------------------
+ * The reference has no multi-device path; its "outer batch" is a sum of independent tape replicas
+ * (dexopt/src/dexlearn.h:440-453) and the only cross-lane operation is the sum behind reverse_batch
+ * (dexopt/src/ops.h:22-34).  Here every rank owns an objective over its share of the rollouts (all ranks but one
+ * with TRX_OBJECTIVE_NO_SCALAR_ROWS) and a communicator; with a communicator attached, every evaluation
+ * (trx_objective_evaluate[_device], each step of trx_objective_gd_steps, trx_objective_hessian_product and the
+ * Gauss-Newton steps built on it) ends with ONE ncclAllReduce(sum) of {loss, gradient[n_x]} on the caller's
+ * stream, so all ranks hold the job's loss and gradient and the device-resident loops need no host in between.
+ * NCCL is bound at run time (libnccl.so.2); without it trx_comm_* fail with TRX_ERR_UNSUPPORTED.
+ *   rank 0:  trx_comm_unique_id(id)  -> broadcast the 128 bytes by any means (MPI, torch.distributed, a file)
+ *   all:     trx_comm_create(id, n_ranks, rank, device, &comm);  trx_objective_set_comm(objective, comm) */
+typedef struct trx_comm trx_comm;
+enum { TRX_COMM_ID_BYTES = 128 };
+trx_status trx_comm_unique_id(uint8_t *id /* TRX_COMM_ID_BYTES */);
+trx_status trx_comm_create(const uint8_t *id, int n_ranks, int rank, int device, trx_comm **out);
+void trx_comm_destroy(trx_comm *c);
+/* sum `count` doubles in place over the ranks (what the objective calls do with {loss, gradient}) */
+trx_status trx_comm_allreduce(trx_comm *c, double *d_values, uint64_t count, void *stream);
+/* the objective does not own the communicator; NULL detaches */
+trx_status trx_objective_set_comm(trx_objective *o, trx_comm *comm);
+
 /* ---- objective assembly (product-side recorder) ------------------------------
  * Stands where dexopt records its problem onto a tape: DexLearn::build ->
  * Program([&]{ _runTraining(); }) (dexopt/src/dexlearn.h:440-453,511-518) followed by

@@ -67,6 +67,12 @@ def lib() -> ctypes.CDLL:
     L.trx_objective_last_times.argtypes = [c.c_void_p, c.POINTER(c.c_float)]
     L.trx_objective_set_profiling.argtypes = [c.c_void_p, c.c_int]
     L.trx_objective_profile_collect.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]
+    L.trx_comm_unique_id.argtypes = [c.c_void_p]
+    L.trx_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_void_p)]
+    L.trx_comm_destroy.argtypes = [c.c_void_p]
+    L.trx_comm_destroy.restype = None
+    L.trx_comm_allreduce.argtypes = [c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
+    L.trx_objective_set_comm.argtypes = [c.c_void_p, c.c_void_p]
     L.trx_dexsyn_build.argtypes = [c.c_char_p, c.POINTER(c.POINTER(c.c_uint8)), c.POINTER(c.c_uint64)]
     L.trx_builder_free.argtypes = [c.POINTER(c.c_uint8)]
     L.trx_builder_free.restype = None

@@ -25,6 +25,7 @@
 #include "trx_fuse.h"
 #include "trx_direct.h"
 #include "vm_exec.cuh"
+#include "trx_comm.h"
 #include "trx_rollout.h"
 
 namespace {
@@ -734,6 +735,7 @@ struct trx_program {
   DevElem *d_elems[3] = {nullptr, nullptr, nullptr};
   uint32_t n_elems[3] = {0, 0, 0};
   int scalar_inputs = TRX_SCALAR_SHARED, scalar_outputs = TRX_SCALAR_SHARED;
+  bool has_scalar_outputs = false;  // any output port of scalar type (one value for all lanes)
   const trx::PortLayout &layout(int which) const {
     return which == TRX_BUF_INPUT ? low.inputs : which == TRX_BUF_PARAMETER ? low.parameters : low.outputs;
   }
@@ -919,6 +921,7 @@ static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int
                                 trx_program **out) {
   // scalar-typed port behaviour across tiles (see trx_b200.h)
   bool reverse_only = p->low.has_reverse && !p->low.has_forward;
+  p->has_scalar_outputs = p->low.outputs.fixed_total > 0;
   p->scalar_inputs = scalar_in != TRX_SCALAR_AUTO ? scalar_in : (reverse_only ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED);
   p->scalar_outputs = scalar_out != TRX_SCALAR_AUTO ? scalar_out : (p->low.has_reverse ? TRX_SCALAR_REDUCE : TRX_SCALAR_SHARED);
 
@@ -1099,8 +1102,27 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) { ret
 
 // upload_constants = false: the caller knows that this memory already holds the program's constants and
 // that nothing has overwritten them (objectives, after their first evaluation)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember which devices have it
+static bool firstUseOnDevice(int device, int which) {
+  static std::mutex mu;
+  static uint64_t done[2] = {0, 0};  // bit = device
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return true;
+  const bool first = !(done[which] >> device & 1);
+  done[which] |= 1ull << device;
+  return first;
+}
+
 static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_, bool upload_constants) {
   if (!p || !m) return fail(TRX_ERR_INVALID, "bad argument");
+  if (p->device != m->device) return fail(TRX_ERR_INVALID, "executable and memory live on different devices");
+  // a program with forward- and reverse-mode instructions (hprop) propagates scalar-typed (lane-independent)
+  // output tangents into the adjoint in every lane tile, so they would count once per tile: refuse instead of
+  // returning a wrong J^T J v (one tile is exact; trx_objective_hessian_product handles any number of tiles)
+  if (p->low.has_forward && p->low.has_reverse && m->n_tiles > 1 && p->has_scalar_outputs)
+    return fail(TRX_ERR_UNSUPPORTED,
+                "forward+reverse program with scalar-typed outputs on more than one lane tile: run it on 8 lanes, or "
+                "use trx_objective_hessian_product");
   cudaStream_t stream = (cudaStream_t)stream_;
   TRX_CUDA(cudaSetDevice(m->device));
   trx_status s = ensureTileStride(m, p->low.memory_size, stream);
@@ -1115,11 +1137,8 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
     uint32_t W = p->low.n_warps;
     size_t smem = (size_t)W * p->low.ring_doubles * sizeof(double);
     if (p->low.ring_doubles) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (firstUseOnDevice(m->device, 0))
         TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-      }
       if (p->low.cta_ring) smem = (size_t)p->low.ring_doubles * sizeof(double);
       trx_vm_kernel<16, true, true, false><<<(unsigned)m->n_tiles, W * 32, smem, stream>>>(
           p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, p->low.ring_doubles, g_trace,
@@ -1128,12 +1147,10 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
     } else if (p->low.page_words == 512 && !p->low.global_pool && staged_streams()) {
       // the product path: stream pages staged in shared memory
       constexpr int kPages = 4;
-      static bool attr_set = false;
       const size_t bytes = (size_t)kStagedWarps * 512 * kPages * sizeof(uint32_t);
-      if (!attr_set) {
+      if (firstUseOnDevice(m->device, 1)) {
         TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        attr_set = true;
       }
       const size_t smem_bytes = (size_t)W * 512 * kPages * sizeof(uint32_t);
       if (g_trace)  // development aid (trx_debug_trace): the instrumented instantiation
@@ -1238,6 +1255,7 @@ struct trx_objective {
   std::vector<cudaEvent_t> prof_events;  // 4 per chunk: before prog, after prog, after prep(+seed), after bprop
   double prof_ms[3] = {0, 0, 0};
   uint64_t prof_count = 0;
+  trx_comm *comm = nullptr;  // not owned: all-reduce of {loss, gradient} after every evaluation
 };
 
 extern "C" {
@@ -1266,7 +1284,8 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
   if (!prog_blob || !prep_blob || !bprop_blob || !out) return fail(TRX_ERR_INVALID, "bad argument");
   *out = nullptr;
   if (lanes == 0 || lanes % 8) return fail(TRX_ERR_INVALID, "lanes must be a positive multiple of 8");
-  std::unique_ptr<trx_objective> o(new trx_objective());
+  // every early return below releases what has been built so far
+  std::unique_ptr<trx_objective, void (*)(trx_objective *)> o(new trx_objective(), trx_objective_destroy);
   o->fused = (flags & TRX_OBJECTIVE_FUSED) != 0;
   o->scalar_rows = (flags & TRX_OBJECTIVE_NO_SCALAR_ROWS) == 0;
   {
@@ -1447,8 +1466,63 @@ trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint
 // The hot path.  x on the device (n_x doubles) -> d_out = [loss, g_0 .. g_{n_x-1}] on the device.
 // Sequence per chunk = GradientDescentSolver::_step's engine calls (solvers/gd.h:50-63):
 // x_prog input+execute, loss = |r|^2, x_prep execute, x_bprop input(r)+execute+output.
+// ---- communicator
+trx_status trx_comm_unique_id(uint8_t *id) {
+  if (!id) return fail(TRX_ERR_INVALID, "bad argument");
+  const trxcomm::Api &nccl = trxcomm::api();
+  if (!nccl.error.empty()) return fail(TRX_ERR_UNSUPPORTED, nccl.error);
+  trxcomm::UniqueId uid;
+  int rc = nccl.GetUniqueId(&uid);
+  if (rc != trxcomm::kNcclSuccess) return fail(TRX_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl.GetErrorString(rc));
+  std::memcpy(id, uid.internal, TRX_COMM_ID_BYTES);
+  return TRX_OK;
+}
+trx_status trx_comm_create(const uint8_t *id, int n_ranks, int rank, int device, trx_comm **out) {
+  if (!id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(TRX_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  const trxcomm::Api &nccl = trxcomm::api();
+  if (!nccl.error.empty()) return fail(TRX_ERR_UNSUPPORTED, nccl.error);
+  TRX_CUDA(cudaSetDevice(device));
+  trxcomm::UniqueId uid;
+  std::memcpy(uid.internal, id, TRX_COMM_ID_BYTES);
+  std::unique_ptr<trx_comm> c(new trx_comm());
+  int rc = nccl.CommInitRank(&c->comm, n_ranks, uid, rank);
+  if (rc != trxcomm::kNcclSuccess) return fail(TRX_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl.GetErrorString(rc));
+  c->n_ranks = n_ranks, c->rank = rank, c->device = device;
+  *out = c.release();
+  return TRX_OK;
+}
+void trx_comm_destroy(trx_comm *c) {
+  if (!c) return;
+  if (c->comm) trxcomm::api().CommDestroy(c->comm);
+  delete c;
+}
+trx_status trx_comm_allreduce(trx_comm *c, double *d_values, uint64_t count, void *stream_) {
+  if (!c || !d_values) return fail(TRX_ERR_INVALID, "bad argument");
+  const trxcomm::Api &nccl = trxcomm::api();
+  int rc = nccl.AllReduce(d_values, d_values, count, trxcomm::kNcclFloat64, trxcomm::kNcclSum, c->comm, (cudaStream_t)stream_);
+  if (rc != trxcomm::kNcclSuccess) return fail(TRX_ERR_CUDA, std::string("ncclAllReduce: ") + nccl.GetErrorString(rc));
+  return TRX_OK;
+}
+trx_status trx_objective_set_comm(trx_objective *o, trx_comm *comm) {
+  if (!o) return fail(TRX_ERR_INVALID, "bad argument");
+  if (comm && comm->device != o->device) return fail(TRX_ERR_INVALID, "communicator and objective live on different devices");
+  o->comm = comm;
+  return TRX_OK;
+}
+
+// this rank's share: d_out = {loss, gradient} over the rollouts of this objective
+static trx_status evaluateLocal(trx_objective *o, const double *d_x, double *d_out, void *stream_);
+
 trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, double *d_out, void *stream_) {
   if (!o || !d_x || !d_out) return fail(TRX_ERR_INVALID, "bad argument");
+  trx_status s = evaluateLocal(o, d_x, d_out, stream_);
+  if (s != TRX_OK || !o->comm) return s;
+  // rollouts are sharded over the ranks: one sum of {loss, gradient}, on the same stream right behind the kernels
+  return trx_comm_allreduce(o->comm, d_out, o->n_x + 1, stream_);
+}
+
+static trx_status evaluateLocal(trx_objective *o, const double *d_x, double *d_out, void *stream_) {
   TRX_CUDA(cudaSetDevice(o->device));
   cudaStream_t stream = (cudaStream_t)stream_;
   if (o->rollout) {

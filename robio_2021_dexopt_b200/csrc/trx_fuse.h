@@ -542,9 +542,9 @@ inline void lowerFused(const trxfile::Program &src, const std::unordered_set<uin
   }
 
   // ---- 4. ports and constants (as lowerProgram)
-  out.inputs = makePortLayout(src.inputs, 8);
-  out.parameters = makePortLayout(src.parameters, 8);
-  out.outputs = makePortLayout(src.outputs, 8);
+  out.inputs = makePortLayout(src.inputs, 8, src.memory_size);
+  out.parameters = makePortLayout(src.parameters, 8, src.memory_size);
+  out.outputs = makePortLayout(src.outputs, 8, src.memory_size);
   for (auto &p : src.constants) {
     if (p.address % 8 || p.size % 8) throw std::runtime_error("constant not 8-byte aligned");
     if (p.offset + p.size > src.const_data.size()) throw std::runtime_error("constant outside the constant blob");

@@ -59,11 +59,16 @@ struct PortLayout {
   uint64_t wideElems(uint64_t lanes) const { return fixed_total + per_lane_total * lanes; }
 };
 
-inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32_t lane_width) {
+inline PortLayout makePortLayout(const std::vector<trxfile::Port> &ports, uint32_t lane_width, uint64_t memory_size) {
   PortLayout L;
-  uint64_t fixed = 0, per_lane = 0;
+  uint64_t fixed = 0, per_lane = 0, packed = 0;
   for (auto &p : ports) {
     if (p.address % 8 || p.size % 8) throw std::runtime_error("port not 8-byte aligned");
+    // a foreign or damaged program must not make the scatter / gather kernels leave the tile image
+    if (p.address + p.size > memory_size || p.address + p.size < p.address) throw std::runtime_error("port outside the memory image");
+    // packed buffers are dense in declaration order (src/core/recorder.cpp:514-572, gradients.cpp:14-20)
+    if (p.offset != packed) throw std::runtime_error("port offsets are not the packed offsets of the declaration order");
+    packed += p.size;
     if (p.lanes == 1) {
       uint32_t n = p.size / 8;
       for (uint32_t c = 0; c < n; c++)
@@ -921,9 +926,9 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   out.stream_begin[W] = out.stream.size();
 
   // ---- 5. ports and constants
-  out.inputs = makePortLayout(src.inputs, tape_lanes == 1 ? 8 : tape_lanes);
-  out.parameters = makePortLayout(src.parameters, tape_lanes == 1 ? 8 : tape_lanes);
-  out.outputs = makePortLayout(src.outputs, tape_lanes == 1 ? 8 : tape_lanes);
+  out.inputs = makePortLayout(src.inputs, tape_lanes == 1 ? 8 : tape_lanes, src.memory_size);
+  out.parameters = makePortLayout(src.parameters, tape_lanes == 1 ? 8 : tape_lanes, src.memory_size);
+  out.outputs = makePortLayout(src.outputs, tape_lanes == 1 ? 8 : tape_lanes, src.memory_size);
   for (auto &p : src.constants) {
     if (p.address % 8 || p.size % 8) throw std::runtime_error("constant not 8-byte aligned");
     if (p.offset + p.size > src.const_data.size()) throw std::runtime_error("constant outside the constant blob");

@@ -50,6 +50,12 @@ class Objective:
         b = np.ascontiguousarray(wide_params, dtype=np.float64)
         check(_native.lib().trx_objective_parameterize(self._h, b.ctypes.data, b.nbytes, None))
 
+    def set_comm(self, comm) -> None:
+        """rollouts sharded over ranks (distributed.Communicator): from now on every evaluation -- also inside the
+        device-resident solver loops -- ends with one all-reduce of {loss, gradient} on its stream"""
+        self._comm = comm  # keep it alive
+        check(_native.lib().trx_objective_set_comm(self._h, comm._h if comm is not None else None))
+
     def evaluate(self, x: np.ndarray):
         """host x -> (loss, gradient); H2D of x and D2H of (loss, g) happen inside"""
         x = np.ascontiguousarray(x, dtype=np.float64)
