@@ -189,7 +189,11 @@ enum {
   TRX_OBJECTIVE_NO_SCALAR_ROWS = 2,
   /* lower x_prog, x_prep, x_bprop as three separate executables (default: x_prep is interleaved into
    * x_prog and the two sweeps are two launches) */
-  TRX_OBJECTIVE_SEPARATE = 4
+  TRX_OBJECTIVE_SEPARATE = 4,
+  /* keep every operand copy of x_prep (default: where a prepare rule only copies an operand, the adjoint reads the
+   * forward slot instead and the copy is dropped, csrc/trx_direct.h).  Needed when a tangent program is attached
+   * (trx_objective_attach_fprop): the forward_* rules read the saved operands as well. */
+  TRX_OBJECTIVE_KEEP_PREP_STATE = 8
 };
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
@@ -225,6 +229,24 @@ trx_status trx_objective_evaluate_device(trx_objective *o, const double *d_x, do
  * (what Solver::loss() returns after step(), solver.cpp:96-103).  Asynchronous on `stream`. */
 trx_status trx_objective_gd_steps(trx_objective *o, double *d_x, double *d_v, double learning_rate, double momentum,
                                   uint32_t n_steps, double *d_losses, void *stream);
+/* ---- Gauss-Newton (LeastSquaresSolver, tractor/include/tractor/solvers/sq.h:57-123) -------------------------
+ * The tangent program x_fprop of the same bundle (buildGradients, gradients.cpp:236-316) is attached to a tape
+ * objective; J^T J v is then x_fprop ; x_bprop on the objective's memory, which is what the reference's x_hprop
+ * executes (gradients.cpp:344-362) and what MatrixReplacement::mul hands to Eigen's conjugate gradients
+ * (core/eigen.h:73-77).  Lane-independent residual rows seed the adjoint once, scalar gradients are summed over
+ * lane tiles and, with a communicator, over ranks.  Tape objectives with all rollouts resident only. */
+trx_status trx_objective_attach_fprop(trx_objective *o, const void *fprop_blob, size_t fprop_bytes);
+/* d_hv[n_x] = J^T J d_v at the point of the last evaluation; device pointers, asynchronous on `stream` */
+trx_status trx_objective_hessian_product(trx_objective *o, const double *d_v, double *d_hv, void *stream);
+/* n_steps of LeastSquaresSolver::_step with x, g, the linear solution and the conjugate-gradient vectors resident
+ * on the device: solve (J^T J + regularization I) d = J^T r by conjugate gradients (Eigen::ConjugateGradient with
+ * the identity preconditioner: zero initial guess, stop at |residual|^2 < tolerance^2 |J^T r|^2 or after
+ * max_linear_iterations, 0 = n_x), then x <- x - step_scaling d.  dexopt: 0.1, 100, 0.5, 1e-9
+ * (dexopt/src/dexopt.cpp:153-160).  d_x[n_x] in/out (device); losses[n_steps] and linear_iterations[n_steps] are
+ * host arrays or NULL.  Synchronous. */
+trx_status trx_objective_sq_steps(trx_objective *o, double *d_x, double regularization, uint32_t max_linear_iterations,
+                                  double step_scaling, double tolerance, uint32_t n_steps, double *losses,
+                                  uint32_t *linear_iterations, void *stream);
 /* CUDA-event times of the last trx_objective_evaluate: {h2d, kernels, d2h} in milliseconds */
 trx_status trx_objective_last_times(const trx_objective *o, float *ms3);
 /* per-program kernel timing with CUDA events on the launching stream: enable, then call

@@ -266,7 +266,7 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
 // Runs K lane tiles through the reference engine and stores the golden arrays.
 static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std::vector<double> &x, size_t n_param_lane,
                        int tiles, uint64_t seed, const std::string &param_kind, int gd_steps = 0,
-                       double learning_rate = 0.01, bool gd_keep_all = true, bool keep_dr = true) {
+                       double learning_rate = 0.01, bool gd_keep_all = true, bool keep_dr = true, int sq_steps = 0) {
   dexsyn::Rng rng(seed);
   RefRunner run(gs);
   size_t nx = portElements(gs.prog.inputs());
@@ -370,6 +370,97 @@ static void goldenRuns(const GradientSet &gs, trxfile::Bundle &bundle, const std
     bundle.arrays.emplace_back("gd/x", iterates);
     bundle.arrays.emplace_back("gd/learning_rate", std::vector<double>{learning_rate});
   }
+
+  // LeastSquaresSolver::_step (tractor/include/tractor/solvers/sq.h:57-123) with dexopt's settings
+  // (dexopt/src/dexopt.cpp:153-160: regularization 0.1, at most 100 linear iterations, step scaling 0.5, tolerance
+  // 1e-9) driven a fixed number of times over all tiles.  The engine work -- x_prog, x_prep, x_bprop and the
+  // Gauss-Newton product x_fprop ; x_bprop (= x_hprop, gradients.cpp:344-362; solvers/base.h:76-85 adds lambda v) --
+  // is the reference's; the linear solver is a restatement of Eigen::ConjugateGradient<MatrixReplacement,
+  // Lower|Upper, IdentityPreconditioner> (Eigen is not in this image: zero initial guess, stop when
+  // |residual|^2 < tol^2 |rhs|^2, iteration cap) -- parity of the linear solve is pinned to this restatement only.
+  if (sq_steps > 0) {
+    const double lambda = 0.1, step_scaling = 0.5, tol = 1e-9;
+    const int max_linear = 100;
+    std::vector<std::unique_ptr<RefRunner>> runs;
+    for (int t = 0; t < tiles; t++) {
+      runs.emplace_back(new RefRunner(gs));
+      runs.back()->parameterize(all_params[t]);
+    }
+    auto dot = [&](const std::vector<double> &a, const std::vector<double> &b) {
+      double sum = 0;
+      for (size_t i = 0; i < a.size(); i++) sum += a[i] * b[i];
+      return sum;
+    };
+    // A v = sum over tiles of J_t^T J_t v (lane-independent rows once) + lambda v, at the current point
+    auto product = [&](const std::vector<double> &v, std::vector<double> &out) {
+      out.assign(nx, 0.0);
+      for (int t = 0; t < tiles; t++) {
+        std::vector<double> dr, h;
+        runs[t]->tangent(v, dr);
+        if (t > 0)
+          for (size_t i = 0; i < dr.size(); i++)
+            if (scalar_out[i]) dr[i] = 0;
+        runs[t]->reverse(dr, h);
+        for (size_t i = 0; i < nx; i++) out[i] += h[i];
+      }
+      for (size_t i = 0; i < nx; i++) out[i] += lambda * v[i];
+    };
+    std::vector<double> xk = x, losses, iterates, cg_its;
+    for (int step = 0; step < sq_steps; step++) {
+      std::vector<double> rhs(nx, 0.0);
+      double loss = 0;
+      for (int t = 0; t < tiles; t++) {
+        std::vector<double> r, g;
+        runs[t]->forward(xk, r);
+        runs[t]->prepare();
+        for (size_t i = 0; i < r.size(); i++) {
+          if (t > 0 && scalar_out[i]) r[i] = 0;
+          loss += r[i] * r[i];
+        }
+        runs[t]->reverse(r, g);
+        for (size_t i = 0; i < nx; i++) rhs[i] += g[i];
+      }
+      // conjugate gradients
+      std::vector<double> sol(nx, 0.0), residual = rhs, p, tmp;
+      int it = 0;
+      const double rhs_norm2 = dot(rhs, rhs);
+      if (rhs_norm2 > 0) {
+        const double threshold = std::max(tol * tol * rhs_norm2, std::numeric_limits<double>::min());
+        double residual_norm2 = dot(residual, residual);
+        if (residual_norm2 >= threshold) {
+          p = residual;
+          double abs_new = dot(residual, p);
+          while (it < max_linear) {
+            product(p, tmp);
+            const double alpha = abs_new / dot(p, tmp);
+            for (size_t i = 0; i < nx; i++) sol[i] += alpha * p[i];
+            for (size_t i = 0; i < nx; i++) residual[i] -= alpha * tmp[i];
+            residual_norm2 = dot(residual, residual);
+            if (residual_norm2 < threshold) break;
+            const double abs_old = abs_new;
+            abs_new = dot(residual, residual);
+            const double beta = abs_new / abs_old;
+            for (size_t i = 0; i < nx; i++) p[i] = residual[i] + beta * p[i];
+            it++;
+          }
+        }
+      }
+      std::vector<double> ab(2 * nx), xn;
+      for (size_t i = 0; i < nx; i++) {
+        ab[i] = xk[i];
+        ab[nx + i] = -sol[i] * step_scaling;
+      }
+      runs[0]->x_accu->run(ab, runs[0]->memory, xn);
+      xk = xn;
+      losses.push_back(loss);
+      cg_its.push_back((double)it);
+      iterates.insert(iterates.end(), xk.begin(), xk.end());
+    }
+    bundle.arrays.emplace_back("sq/loss", losses);
+    bundle.arrays.emplace_back("sq/x", iterates);
+    bundle.arrays.emplace_back("sq/cg_iterations", cg_its);
+    bundle.arrays.emplace_back("sq/settings", std::vector<double>{lambda, (double)max_linear, step_scaling, tol});
+  }
 }
 
 static int cmdRecord(const std::string &path, const std::map<std::string, std::string> &kv) {
@@ -407,7 +498,7 @@ static int cmdRecord(const std::string &path, const std::map<std::string, std::s
   if (tiles > 0)
     goldenRuns(gs, bundle, x, n_param_lane, tiles, (uint64_t)getI(kv, "seed", 20211227) + 77, problem,
                (int)getI(kv, "gd_steps", 0), getD(kv, "lr", 0.01), getS(kv, "gd_keep", "all") == "all",
-               getI(kv, "keep_dr", 1) != 0);
+               getI(kv, "keep_dr", 1) != 0, (int)getI(kv, "sq_steps", 0));
   else bundle.arrays.emplace_back("x", x);
   trxfile::writeBundle(bundle, path);
   std::cerr << meta;

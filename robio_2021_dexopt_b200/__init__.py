@@ -9,4 +9,4 @@ from .engine import CudaEngine, Executable, Memory, kernel_launch_count  # noqa:
 from ._native import TrxError  # noqa: F401
 from . import trxfile  # noqa: F401
 from .builder import build_dexsyn  # noqa: F401
-from .solver import GradientDescentSolver, Objective, RolloutObjective  # noqa: F401
+from .solver import GradientDescentSolver, LeastSquaresSolver, Objective, RolloutObjective  # noqa: F401

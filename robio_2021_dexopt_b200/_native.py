@@ -67,6 +67,10 @@ def lib() -> ctypes.CDLL:
     L.trx_objective_last_times.argtypes = [c.c_void_p, c.POINTER(c.c_float)]
     L.trx_objective_set_profiling.argtypes = [c.c_void_p, c.c_int]
     L.trx_objective_profile_collect.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_uint64)]
+    L.trx_objective_attach_fprop.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t]
+    L.trx_objective_hessian_product.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p]
+    L.trx_objective_sq_steps.argtypes = [c.c_void_p, c.c_void_p, c.c_double, c.c_uint32, c.c_double, c.c_double, c.c_uint32,
+                                         c.c_void_p, c.c_void_p, c.c_void_p]
     L.trx_comm_unique_id.argtypes = [c.c_void_p]
     L.trx_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_void_p)]
     L.trx_comm_destroy.argtypes = [c.c_void_p]

@@ -15,6 +15,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <limits>
+#include <cmath>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -720,6 +722,44 @@ __global__ void trx_gd_update_kernel(double *x, double *v, const double *out, ui
   }
 }
 
+// ---- Gauss-Newton pieces (solvers/sq.h, solvers/base.h:76-85)
+// after the tangent sweep: scalar-typed (lane-independent) output tangents are the same in every tile and seed the
+// adjoint once, in tile 0 of the rank that owns those rows (the same rule as trx_seed_kernel)
+__global__ void trx_mask_scalar_kernel(const DevElem *__restrict__ elems, uint32_t n, double *mem, uint64_t tile_stride,
+                                       int keep_in_tile0) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t tile = blockIdx.y;
+  const DevElem e = elems[i];
+  if (e.lane == 0xff && (tile != 0 || !keep_in_tile0)) mem[tile * tile_stride + e.idx] = 0.0;
+}
+// out[slot] = a . b ; one CTA, fixed summation order (deterministic)
+__global__ void trx_dot_kernel(const double *__restrict__ a, const double *__restrict__ b, uint32_t n, double *out) {
+  __shared__ double red[1024];
+  double sum = 0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sum += a[i] * b[i];
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (uint32_t w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+// y <- y + alpha x   (and, when z is given, z <- z + beta x)
+__global__ void trx_axpy2_kernel(double *y, double alpha, const double *__restrict__ x, double *z, double beta, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double xi = x[i];
+  y[i] += alpha * xi;
+  if (z) z[i] += beta * xi;
+}
+// p <- r + beta p
+__global__ void trx_cg_direction_kernel(double *p, const double *__restrict__ r, double beta, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = r[i] + beta * p[i];
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ objects
@@ -1256,6 +1296,12 @@ struct trx_objective {
   double prof_ms[3] = {0, 0, 0};
   uint64_t prof_count = 0;
   trx_comm *comm = nullptr;  // not owned: all-reduce of {loss, gradient} after every evaluation
+  // Gauss-Newton (LeastSquaresSolver): tangent executable and the conjugate-gradient vectors, all on the device
+  trx_program *fprop = nullptr;
+  bool keeps_prep_state = false;  // x_prep's operand copies are all there (tangent rules read them)
+  double *d_cg = nullptr;        // 5 x n_x: rhs, solution, residual, direction, product
+  double *d_scal = nullptr;      // dot products
+  double *h_scal = nullptr;      // pinned
 };
 
 extern "C" {
@@ -1296,7 +1342,9 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       trxfile::decodeProgram(bprop_blob, bprop_bytes, p_bprop);
       // the adjoint reads forward operands in place instead of through x_prep's copies (trx_direct.h)
       static int direct_env = getenv("TRX_DIRECT") ? atoi(getenv("TRX_DIRECT")) : 1;
-      if (direct_env && !o->fused) trx::directPrepare(p_prep, p_bprop, o->direct);
+      // (not when a tangent program will be attached: forward_* rules read x_prep's saved operands too)
+      if (direct_env && !o->fused && !(flags & TRX_OBJECTIVE_KEEP_PREP_STATE)) trx::directPrepare(p_prep, p_bprop, o->direct);
+      o->keeps_prep_state = !(direct_env && !o->fused && !(flags & TRX_OBJECTIVE_KEEP_PREP_STATE));
       static int static_env = getenv("TRX_STATIC_CONSTS") ? atoi(getenv("TRX_STATIC_CONSTS")) : 1;
       o->consts_static = static_env && trx::constantsAreNeverWritten({&p_prog, &p_prep, &p_bprop});
     } catch (const std::exception &e) {
@@ -1387,6 +1435,10 @@ void trx_objective_destroy(trx_objective *o) {
   trx_program_destroy(o->prog);
   trx_program_destroy(o->prep);
   trx_program_destroy(o->bprop);
+  trx_program_destroy(o->fprop);
+  cudaFree(o->d_cg);
+  cudaFree(o->d_scal);
+  if (o->h_scal) cudaFreeHost(o->h_scal);
   trx_memory_destroy(o->mem);
   cudaFree(o->d_x);
   cudaFree(o->d_params);
@@ -1646,6 +1698,158 @@ trx_status trx_objective_gd_steps(trx_objective *o, double *d_x, double *d_v, do
     g_launches++;
   }
   TRX_CUDA(cudaGetLastError());
+  return TRX_OK;
+}
+
+// ---- Gauss-Newton: tangent sweep, J^T J v, LeastSquaresSolver::_step
+trx_status trx_objective_attach_fprop(trx_objective *o, const void *fprop_blob, size_t fprop_bytes) {
+  if (!o || !fprop_blob) return fail(TRX_ERR_INVALID, "bad argument");
+  if (o->rollout)
+    return fail(TRX_ERR_UNSUPPORTED, "the re-rolled objective has no tangent sweep: Gauss-Newton products need the tape objective");
+  if (o->fused) return fail(TRX_ERR_UNSUPPORTED, "fused lowering keeps no tangent slots");
+  if (!o->keeps_prep_state)
+    return fail(TRX_ERR_INVALID,
+                "this objective dropped x_prep's operand copies (the adjoint reads forward values in place); create it "
+                "with TRX_OBJECTIVE_KEEP_PREP_STATE: the tangent rules read the saved operands");
+  trxfile::Program p_fprop;
+  try {
+    trxfile::decodeProgram(fprop_blob, fprop_bytes, p_fprop);
+  } catch (const std::exception &e) {
+    return fail(TRX_ERR_INVALID, e.what());
+  }
+  trx_program *raw = nullptr;
+  trx_status s = createFromFile(p_fprop, o->device, TRX_SCALAR_SHARED, TRX_SCALAR_SHARED, &raw);
+  if (s != TRX_OK) return s;
+  if (raw->low.inputs.elems.size() != o->prog->low.inputs.elems.size() ||
+      raw->low.outputs.elems.size() != o->bprop->low.inputs.elems.size()) {
+    trx_program_destroy(raw);
+    return fail(TRX_ERR_INVALID, "fprop ports do not mirror the objective's");
+  }
+  for (size_t i = 0; i < raw->low.outputs.elems.size(); i++)
+    if (raw->low.outputs.elems[i].idx != o->bprop->low.inputs.elems[i].idx) {
+      // hprop = fprop ; bprop works because the tangent of an output lands in the adjoint's seed slot (gradients.cpp:344-362)
+      trx_program_destroy(raw);
+      return fail(TRX_ERR_INVALID, "fprop outputs are not the adjoint's seed slots");
+    }
+  trx_program_destroy(o->fprop);
+  o->fprop = raw;
+  // the tangent sweep writes slots of its own; the objective's constants are uploaded by every execute again
+  o->consts_static = false;
+  o->consts_resident = false;
+  TRX_CUDA(cudaSetDevice(o->device));
+  return ensureTileStride(o->mem, raw->low.memory_size, nullptr);
+}
+
+// d_hv[n_x] = J^T J d_v at the point of the last evaluation (x_prog and x_prep state are in the memory image):
+// x_fprop->input(v); execute; x_bprop->execute; output -- the reference's x_hprop (core/eigen.h:73-77), with the
+// lane-independent rows seeded once and the sum over tiles (and ranks) that completes reverse_batch.
+trx_status trx_objective_hessian_product(trx_objective *o, const double *d_v, double *d_hv, void *stream_) {
+  if (!o || !d_v || !d_hv) return fail(TRX_ERR_INVALID, "bad argument");
+  if (!o->fprop) return fail(TRX_ERR_INVALID, "no tangent program: call trx_objective_attach_fprop first");
+  if (o->n_chunks != 1)
+    return fail(TRX_ERR_UNSUPPORTED, "Gauss-Newton products need all rollouts resident (one chunk): raise max_device_bytes");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  trx_memory *m = o->mem;
+  trx_status s = scatterDevice(o->fprop, m, TRX_BUF_INPUT, d_v, o->n_x * 8, stream, o->lanes, 0);
+  if (s != TRX_OK) return s;
+  if ((s = executeImpl(o->fprop, m, stream_, true)) != TRX_OK) return s;
+  {
+    const uint32_t n = o->bprop->n_elems[TRX_BUF_INPUT];
+    trx_mask_scalar_kernel<<<dim3((n + 255) / 256, (unsigned)m->n_tiles), 256, 0, stream>>>(
+        o->bprop->d_elems[TRX_BUF_INPUT], n, m->d_mem, m->tile_stride, o->scalar_rows ? 1 : 0);
+    g_launches++;
+  }
+  if ((s = executeImpl(o->bprop, m, stream_, true)) != TRX_OK) return s;
+  {
+    const uint32_t n = o->bprop->n_elems[TRX_BUF_OUTPUT];
+    trx_gather_kernel<<<dim3((n + 255) / 256, 1), 256, 0, stream>>>(o->bprop->d_elems[TRX_BUF_OUTPUT], n, d_hv, o->lanes, 0,
+                                                                   m->d_mem, m->tile_stride, (uint32_t)m->n_tiles, 1, 0);
+    g_launches++;
+  }
+  TRX_CUDA(cudaGetLastError());
+  if (o->comm) return trx_comm_allreduce(o->comm, d_hv, o->n_x, stream_);
+  return TRX_OK;
+}
+
+// LeastSquaresSolver::_step (solvers/sq.h:57-123) n_steps times with the vectors resident on the device:
+//   r = x_prog(x), loss = |r|^2, x_prep, g = x_bprop(r)                       (trx_objective_evaluate_device)
+//   solve (J^T J + lambda I) d = g by conjugate gradients                      (Eigen::ConjugateGradient, identity
+//     preconditioner, zero initial guess, stop when |residual|^2 < tol^2 |g|^2 or after max_linear_iterations;
+//     product = trx_objective_hessian_product + lambda v, solvers/base.h:76-85)
+//   x <- x (+) (-step_scaling d)                                               (sq.h:101,121-122; scalar inputs: add)
+// The host sees two dot products per linear iteration and nothing else.  losses[n_steps] (host, may be null): the
+// loss before each update; linear_iterations[n_steps] (host, may be null).  Synchronous.
+trx_status trx_objective_sq_steps(trx_objective *o, double *d_x, double regularization, uint32_t max_linear_iterations,
+                                  double step_scaling, double tolerance, uint32_t n_steps, double *losses,
+                                  uint32_t *linear_iterations, void *stream_) {
+  if (!o || !d_x) return fail(TRX_ERR_INVALID, "bad argument");
+  if (!o->fprop) return fail(TRX_ERR_INVALID, "no tangent program: call trx_objective_attach_fprop first");
+  TRX_CUDA(cudaSetDevice(o->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const uint32_t n = (uint32_t)o->n_x;
+  if (!o->d_cg) {
+    TRX_CUDA(cudaMalloc(&o->d_cg, (size_t)5 * n * sizeof(double)));
+    TRX_CUDA(cudaMalloc(&o->d_scal, 8 * sizeof(double)));
+    TRX_CUDA(cudaMallocHost(&o->h_scal, 8 * sizeof(double)));
+  }
+  double *rhs = o->d_cg, *sol = rhs + n, *res = sol + n, *dir = res + n, *tmp = dir + n;
+  const unsigned blocks = (n + 255) / 256;
+  auto dot = [&](const double *a, const double *b, double &value) -> trx_status {
+    trx_dot_kernel<<<1, 1024, 0, stream>>>(a, b, n, o->d_scal);
+    g_launches++;
+    TRX_CUDA(cudaMemcpyAsync(o->h_scal, o->d_scal, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    TRX_CUDA(cudaStreamSynchronize(stream));
+    value = o->h_scal[0];
+    return TRX_OK;
+  };
+  const uint32_t max_it = max_linear_iterations ? max_linear_iterations : n;  // sq.h:86-90
+  for (uint32_t step = 0; step < n_steps; step++) {
+    trx_status s = trx_objective_evaluate_device(o, d_x, o->d_out, stream_);
+    if (s != TRX_OK) return s;
+    TRX_CUDA(cudaMemcpyAsync(rhs, o->d_out + 1, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    TRX_CUDA(cudaMemcpyAsync(res, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    TRX_CUDA(cudaMemsetAsync(sol, 0, n * sizeof(double), stream));
+    TRX_CUDA(cudaMemcpyAsync(o->h_scal + 1, o->d_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    double rhs_norm2 = 0;
+    if ((s = dot(rhs, rhs, rhs_norm2)) != TRX_OK) return s;
+    if (losses) losses[step] = o->h_scal[1];
+    if (!std::isfinite(rhs_norm2)) return fail(TRX_ERR_INVALID, "gradient not finite (sq.h:76)");
+    uint32_t it = 0;
+    if (rhs_norm2 > 0) {
+      const double threshold = std::max(tolerance * tolerance * rhs_norm2, std::numeric_limits<double>::min());
+      double residual_norm2 = rhs_norm2;
+      if (residual_norm2 >= threshold) {
+        TRX_CUDA(cudaMemcpyAsync(dir, res, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        double abs_new = residual_norm2;
+        while (it < max_it) {
+          if ((s = trx_objective_hessian_product(o, dir, tmp, stream_)) != TRX_OK) return s;
+          if (regularization > 0) {
+            trx_axpy2_kernel<<<blocks, 256, 0, stream>>>(tmp, regularization, dir, nullptr, 0.0, n);
+            g_launches++;
+          }
+          double p_dot_tmp = 0;
+          if ((s = dot(dir, tmp, p_dot_tmp)) != TRX_OK) return s;
+          const double alpha = abs_new / p_dot_tmp;
+          trx_axpy2_kernel<<<blocks, 256, 0, stream>>>(sol, alpha, dir, nullptr, 0.0, n);
+          trx_axpy2_kernel<<<blocks, 256, 0, stream>>>(res, -alpha, tmp, nullptr, 0.0, n);
+          g_launches += 2;
+          if ((s = dot(res, res, residual_norm2)) != TRX_OK) return s;
+          if (residual_norm2 < threshold) break;
+          const double abs_old = abs_new;
+          abs_new = residual_norm2;
+          trx_cg_direction_kernel<<<blocks, 256, 0, stream>>>(dir, res, abs_new / abs_old, n);
+          g_launches++;
+          it++;
+        }
+      }
+    }
+    if (linear_iterations) linear_iterations[step] = it;
+    trx_axpy2_kernel<<<blocks, 256, 0, stream>>>(d_x, -step_scaling, sol, nullptr, 0.0, n);
+    g_launches++;
+  }
+  TRX_CUDA(cudaGetLastError());
+  TRX_CUDA(cudaStreamSynchronize(stream));
   return TRX_OK;
 }
 

@@ -24,18 +24,20 @@ class Objective:
     """objective + gradient over R rollouts of a recorded problem (prog/prep/bprop of one bundle)"""
 
     def __init__(self, engine: CudaEngine, bundle: trxfile.Bundle, lanes: int, max_device_bytes: int = 0,
-                 fused: bool = False, scalar_rows: bool = True, separate: bool = False):
+                 fused: bool = False, scalar_rows: bool = True, separate: bool = False, gauss_newton: bool = False):
         """default: x_prep interleaved into x_prog, level-scheduled (csrc/trx_lower.h), two launches per chunk.
         separate=True: prog, prep, bprop as three generic executables.  fused=True: experimental chain
         scheduling with on-chip slot rings (csrc/trx_fuse.h).
-        scalar_rows=False: this rank does not count the lane-independent residual rows (multi-GPU)"""
+        scalar_rows=False: this rank does not count the lane-independent residual rows (multi-GPU).
+        gauss_newton=True: keep x_prep's operand copies so that a tangent program can be attached (attach_fprop)"""
         self.engine = engine
         self._h = ctypes.c_void_p()
         blobs = [bundle.programs[n] for n in ("prog", "prep", "bprop")]
         bufs = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
         check(_native.lib().trx_objective_create(bufs[0], len(blobs[0]), bufs[1], len(blobs[1]), bufs[2], len(blobs[2]),
                                                  lanes, max_device_bytes, engine.device,
-                                                 (1 if fused else 0) | (0 if scalar_rows else 2) | (4 if separate else 0),
+                                                 (1 if fused else 0) | (0 if scalar_rows else 2) | (4 if separate else 0) |
+                                                 (8 if gauss_newton else 0),
                                                  ctypes.byref(self._h)))
         self.lanes = lanes
         self.n_x = self.info("n_x")
@@ -76,6 +78,34 @@ class Objective:
                                                    ctypes.c_double(learning_rate), ctypes.c_double(momentum),
                                                    ctypes.c_uint32(n_steps), ctypes.c_void_p(d_losses_ptr),
                                                    ctypes.c_void_p(stream)))
+
+    def attach_fprop(self, bundle: trxfile.Bundle) -> None:
+        """the tangent program of the same bundle: enables hessian_product and LeastSquaresSolver (tape objectives)"""
+        blob = bundle.programs["fprop"]
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        check(_native.lib().trx_objective_attach_fprop(self._h, buf, len(blob)))
+
+    def hessian_product(self, v: np.ndarray) -> np.ndarray:
+        """J^T J v at the point of the last evaluate() -- the reference's x_hprop (core/eigen.h:73-77)"""
+        import torch
+        dev = torch.device("cuda", self.engine.device)
+        d_v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev)
+        d_hv = torch.empty(self.n_x, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(_native.lib().trx_objective_hessian_product(self._h, ctypes.c_void_p(d_v.data_ptr()),
+                                                          ctypes.c_void_p(d_hv.data_ptr()), ctypes.c_void_p(stream)))
+        return d_hv.cpu().numpy()
+
+    def sq_steps(self, d_x_ptr: int, regularization: float, max_linear_iterations: int, step_scaling: float,
+                 tolerance: float, n_steps: int, stream: int = 0):
+        """n_steps LeastSquaresSolver steps with all vectors on the device; returns (losses, linear iterations)"""
+        losses = np.zeros(max(1, n_steps))
+        its = np.zeros(max(1, n_steps), dtype=np.uint32)
+        check(_native.lib().trx_objective_sq_steps(self._h, ctypes.c_void_p(d_x_ptr), ctypes.c_double(regularization),
+                                                   ctypes.c_uint32(max_linear_iterations), ctypes.c_double(step_scaling),
+                                                   ctypes.c_double(tolerance), ctypes.c_uint32(n_steps),
+                                                   losses.ctypes.data, its.ctypes.data, ctypes.c_void_p(stream)))
+        return losses[:n_steps], its[:n_steps]
 
     def set_profiling(self, enable: bool) -> None:
         check(_native.lib().trx_objective_set_profiling(self._h, 1 if enable else 0))
@@ -177,4 +207,48 @@ class GradientDescentSolver:
         return self._loss
 
     def scatter(self) -> np.ndarray:  # solver.cpp:62-66
+        return self.x.copy()
+
+
+class LeastSquaresSolver:
+    """LeastSquaresSolver (solvers/sq.h:14-123): Gauss-Newton steps, (J^T J + lambda I) d = J^T r solved by conjugate
+    gradients over the Gauss-Newton product (core/eigen.h:53-83, solvers/base.h:76-85), x <- x - step_scaling d.
+    Defaults are dexopt's "sq" solver (dexopt/src/dexopt.cpp:153-160).  The objective must be a tape objective with
+    its tangent program attached (Objective.attach_fprop); everything runs on the device
+    (trx_objective_sq_steps)."""
+
+    def __init__(self, objective: Objective, regularization: float = 0.1, max_linear_iterations: int = 100,
+                 step_scaling: float = 0.5, tolerance: float = 1e-9):
+        self.objective = objective
+        self.regularization = regularization
+        self.max_linear_iterations = max_linear_iterations
+        self.step_scaling = step_scaling
+        self.tolerance = tolerance
+        self.x: Optional[np.ndarray] = None
+        self._loss = float("nan")
+        self.linear_iterations = []
+
+    def gather(self, x0: np.ndarray) -> None:
+        self.x = np.array(x0, dtype=np.float64)
+
+    def steps(self, n_steps: int) -> np.ndarray:
+        import torch
+        dev = torch.device("cuda", self.objective.engine.device)
+        d_x = torch.from_numpy(self.x).to(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        losses, its = self.objective.sq_steps(d_x.data_ptr(), self.regularization, self.max_linear_iterations,
+                                              self.step_scaling, self.tolerance, n_steps, stream)
+        self.x = d_x.cpu().numpy()
+        self.linear_iterations.extend(int(i) for i in its)
+        if n_steps:
+            self._loss = float(losses[-1])
+        return losses
+
+    def step(self) -> float:
+        return float(self.steps(1)[0])
+
+    def loss(self) -> float:
+        return self._loss
+
+    def scatter(self) -> np.ndarray:
         return self.x.copy()

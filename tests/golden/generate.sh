@@ -22,4 +22,6 @@ $R record $G/rollout_handarm_h64.trxb problem=dexsyn kind=handarm hidden=64 fram
 $R record $G/rollout_hand8_linear.trxb problem=dexsyn kind=hand8 hidden=0 frames=5 tiles=2 gd_steps=10 programs=0 gd_keep=last keep_dr=0
 $R record $G/rollout_chain30.trxb problem=dexsyn kind=chain joints=30 contacts=16 hidden=16 frames=3 tiles=1 programs=0 keep_dr=0
 $R record $G/rollout_handarm_long.trxb problem=dexsyn kind=handarm hidden=8 frames=24 tiles=1 programs=0 keep_dr=0
+# LeastSquaresSolver iterates of the dexsyn_small problem (values only): reference engine work, restated Eigen CG
+$R record $G/sq_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 sq_steps=3 programs=0 keep_dr=0
 ls -la $G

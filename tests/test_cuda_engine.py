@@ -344,3 +344,54 @@ def test_full_size_rollout_sharding_and_determinism(cuda_engine):
     assert chunks >= 2
     assert abs(c[0] - loss) <= 1e-12 * abs(loss)
     parity.assert_close(c[1], g, "gradient of the chunked walk", rtol=1e-9, atol=1e-12)
+
+
+# ------------------------------------------------------------------ Gauss-Newton (LeastSquaresSolver)
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fuse_dense", [0, 1])
+def test_hessian_product_matches_reference(cuda_engine, golden, fuse_dense):
+    """J^T J dx over two lane tiles (lane-independent rows once) against the reference's x_fprop ; x_bprop"""
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("dexsyn_small.trxb.xz")
+    mine = pkg.build_dexsyn(frames=3, hidden=4, extra_fixed=4, fuse_dense=fuse_dense)
+    obj = pkg.Objective(cuda_engine, mine, lanes=16, separate=True, gauss_newton=True)
+    obj.attach_fprop(mine)
+    obj.parameterize(trxfile.tiles_to_wide(mine.view("prog").parameters, parity.tile_arrays(ref, "params")))
+    loss, g = obj.evaluate(ref.arrays["x"])
+    parity.assert_close(g, ref.arrays["g_total"], "gradient")
+    h = obj.hessian_product(ref.arrays["dx"])
+    parity.assert_close(h, ref.arrays["h_total"], "J^T J dx", rtol=1e-10, atol=1e-12)
+    # and again: the product leaves the linearisation point intact
+    parity.assert_close(obj.hessian_product(ref.arrays["dx"]), ref.arrays["h_total"], "J^T J dx (second call)",
+                        rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_least_squares_iterates_match_reference(cuda_engine, golden):
+    """three LeastSquaresSolver steps (dexopt's settings: lambda 0.1, <= 100 linear iterations, step 0.5, tolerance
+    1e-9) on the device against the reference engine driven by the restated Eigen conjugate gradients
+    (oracle/ref_build/ref_tool.cpp sq_steps).  Tolerance: the conjugate-gradient recurrences amplify the rounding
+    differences of the dot products (parallel tree sums here, sequential there), so iterates are compared at 1e-7
+    relative to the largest element and the iteration counts may differ by one; losses at 1e-9."""
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("sq_small.trxb")
+    lam, max_lin, step, tol = ref.arrays["sq/settings"]
+    mine = pkg.build_dexsyn(frames=3, hidden=4, extra_fixed=4, fuse_dense=1)
+    obj = pkg.Objective(cuda_engine, mine, lanes=16, separate=True, gauss_newton=True)
+    obj.attach_fprop(mine)
+    obj.parameterize(trxfile.tiles_to_wide(mine.view("prog").parameters, parity.tile_arrays(ref, "params")))
+    solver = pkg.LeastSquaresSolver(obj, lam, int(max_lin), step, tol)
+    solver.gather(ref.arrays["x"])
+    n_x = ref.arrays["x"].size
+    want_x = ref.arrays["sq/x"].reshape(-1, n_x)
+    for k in range(want_x.shape[0]):
+        loss = solver.step()
+        want_loss = float(ref.arrays["sq/loss"][k])
+        assert abs(loss - want_loss) <= 1e-9 * abs(want_loss) * (1 if k == 0 else 100), (k, loss, want_loss)
+        assert abs(solver.linear_iterations[k] - int(ref.arrays["sq/cg_iterations"][k])) <= 1
+        err = np.max(np.abs(solver.scatter() - want_x[k])) / np.max(np.abs(want_x[k]))
+        assert err <= 1e-7, (k, err)
+    assert solver.loss() < float(ref.arrays["sq/loss"][0])
