@@ -161,6 +161,11 @@ trx_status trx_parameterize_device(const trx_program *p, trx_memory *m, const vo
                                    void *stream);
 trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed, uint64_t bytes, void *stream);
 
+/* In-tape random operators (add_random_normal, add_random_uniform, dropout2: dexopt/src/ops.h:120-204) draw fresh
+ * values at every execute, as the reference's do; here every draw is a function of (seed, execute counter, rollout,
+ * instruction) -- Philox4x32-10 -- so a run can be repeated: setting the seed restarts the execute counter. */
+void trx_set_random_seed(uint64_t seed);
+
 /* number of kernels this library has launched since load (for launch accounting) */
 uint64_t trx_kernel_launch_count(void);
 

@@ -790,6 +790,7 @@ struct trx_memory {
   uint64_t stage_elems = 0;
   double *h_stage = nullptr;  // pinned
   uint64_t h_stage_elems = 0;
+  uint64_t rng_lane_base = 0;  // rollout of lane 0 of tile 0 (objectives that walk their rollouts in chunks)
 };
 
 namespace {
@@ -1142,6 +1143,8 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) { ret
 
 // upload_constants = false: the caller knows that this memory already holds the program's constants and
 // that nothing has overwritten them (objectives, after their first evaluation)
+static std::atomic<uint64_t> g_rng_seed{0x9E3779B97F4A7C15ull}, g_rng_epoch{0};
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember which devices have it
 static bool firstUseOnDevice(int device, int which) {
   static std::mutex mu;
@@ -1167,6 +1170,16 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
   TRX_CUDA(cudaSetDevice(m->device));
   trx_status s = ensureTileStride(m, p->low.memory_size, stream);
   if (s != TRX_OK) return s;
+  if (p->low.draws_random) {
+    // in-tape random draws (vm_exec.cuh): fresh values at every execute, reproducible from the seed
+    trxvm::RngState st;
+    st.seed = g_rng_seed.load();
+    st.epoch = ++g_rng_epoch;
+    st.base = m->d_mem;
+    st.tile_stride = m->tile_stride;
+    st.lane_base = m->rng_lane_base;
+    TRX_CUDA(cudaMemcpyToSymbolAsync(trxvm::g_rng_dev, &st, sizeof(st), 0, cudaMemcpyHostToDevice, stream));
+  }
   uint32_t nc = upload_constants ? (uint32_t)p->low.const_idx.size() : 0;
   if (nc) {
     dim3 grid((nc + 255) / 256, (unsigned)m->n_tiles);
@@ -1518,6 +1531,12 @@ trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint
 // The hot path.  x on the device (n_x doubles) -> d_out = [loss, g_0 .. g_{n_x-1}] on the device.
 // Sequence per chunk = GradientDescentSolver::_step's engine calls (solvers/gd.h:50-63):
 // x_prog input+execute, loss = |r|^2, x_prep execute, x_bprop input(r)+execute+output.
+// seed of the in-tape random operators; the execute counter restarts, so a run is reproducible from here
+void trx_set_random_seed(uint64_t seed) {
+  g_rng_seed.store(seed);
+  g_rng_epoch.store(0);
+}
+
 // ---- communicator
 trx_status trx_comm_unique_id(uint8_t *id) {
   if (!id) return fail(TRX_ERR_INVALID, "bad argument");
@@ -1595,6 +1614,7 @@ static trx_status evaluateLocal(trx_objective *o, const double *d_x, double *d_o
     }
     s = scatterDevice(o->prog, m, TRX_BUF_INPUT, d_x, o->n_x * 8, stream, o->lanes, c * o->chunk_lanes);
     if (s != TRX_OK) return s;
+    m->rng_lane_base = c * o->chunk_lanes;
     cudaEvent_t *pe = o->profiling ? &o->prof_events[c * 4] : nullptr;
     if (pe) cudaEventRecord(pe[0], stream);
     // constants: uploaded by every execute as the reference does (simple.cpp:27-30), except when this

@@ -161,6 +161,77 @@ TRX_HD void stt(const C &c, int k, int o, const TwistV &t) {
   stv(c, k, o + 3, t.r);
 }
 
+// BatchScalar-typed output (one double for all lanes): the first lane stores it
+template <class C>
+TRX_HD void sts(const C &c, int k, double v) {
+  if (c.LO() == 0) c.m[argword(c, k)] = v;
+}
+
+// ---- in-tape random numbers (dexopt/src/ops.h:120-204: add_random_normal, add_random_uniform, dropout2)
+// The reference draws from a thread_local std::mt19937 seeded from rand() -- fresh, unreproducible values at every
+// execute.  Here a draw is a pure function of (seed, execute counter, rollout, instruction): Philox4x32-10
+// (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC11) with
+//   counter = {rollout lo, rollout hi, output slot of the instruction, draw index}, key = {seed ^ epoch}.
+// The host sets the state before every execute of a tape that draws (trx_engine.cu executeImpl).
+struct RngState {
+  unsigned long long seed = 0x9E3779B97F4A7C15ull, epoch = 0;
+  const double *base = nullptr;        // first tile of the memory the program runs on
+  unsigned long long tile_stride = 1;  // doubles
+  unsigned long long lane_base = 0;    // rollout of lane 0 of tile 0
+};
+#ifdef __CUDACC__
+__device__ RngState g_rng_dev;
+#endif
+// host executions of the operators (tests/emu): one state per process, whichever copy of these inline functions
+// the dynamic linker picks
+inline RngState &rngHostState() {
+  static RngState state;
+  return state;
+}
+
+TRX_HD void philox4x32_10(const uint32_t (&ctr)[4], const uint32_t (&key)[2], uint32_t (&out)[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int round = 0; round < 10; round++) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1,
+                   n3 = (uint32_t)p0;
+    c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+// two uniforms in [0, 1) with 53 random bits each, for output argument kout of the running instruction
+template <class C>
+TRX_HD void rng_uniform2(const C &c, int kout, double &u0, double &u1) {
+#ifdef __CUDA_ARCH__
+  const RngState &r = g_rng_dev;
+#else
+  const RngState &r = rngHostState();
+#endif
+  const unsigned long long tile = (unsigned long long)(c.m - r.base) / r.tile_stride;
+  const unsigned long long rollout = r.lane_base + tile * 8 + (unsigned)c.LO();
+  const unsigned long long k = r.seed ^ (r.epoch * 0xD1B54A32D192ED03ull);
+  const uint32_t ctr[4] = {(uint32_t)rollout, (uint32_t)(rollout >> 32), argword(c, kout), 0u};
+  const uint32_t key[2] = {(uint32_t)k, (uint32_t)(k >> 32)};
+  uint32_t o[4];
+  philox4x32_10(ctr, key, o);
+  u0 = (double)((((unsigned long long)o[0] << 32) | o[1]) >> 11) * (1.0 / 9007199254740992.0);
+  u1 = (double)((((unsigned long long)o[2] << 32) | o[3]) >> 11) * (1.0 / 9007199254740992.0);
+}
+template <class C>
+TRX_HD double rng_uniform(const C &c, int kout) {
+  double u0, u1;
+  rng_uniform2(c, kout, u0, u1);
+  return u0;
+}
+// standard normal (Box-Muller on one Philox block)
+template <class C>
+TRX_HD double rng_normal(const C &c, int kout) {
+  double u0, u1;
+  rng_uniform2(c, kout, u0, u1);
+  return sqrt(-2.0 * log(1.0 - u0)) * cos(6.283185307179586476925286766559 * u1);
+}
+
 // number of arguments in a signature string (tokens separated by single blanks)
 TRX_HD constexpr int sigArgCount(const char *sig) {
   int n = 0;

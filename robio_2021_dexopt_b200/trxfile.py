@@ -129,6 +129,31 @@ def parse_program(payload: bytes) -> ProgramView:
                        const_data)
 
 
+def encode_program(lane_width: int, memory_size: int, ops, instructions, inputs=(), parameters=(), outputs=(),
+                   constants=(), const_data: bytes = b"") -> bytes:
+    """program payload (the inverse of parse_program) from plain Python values:
+    ops = [(name, [(size, is_input, lanes, elem), ...])], instructions = [(op index, [byte address, ...])],
+    ports = [Port]; used to hand-write small tapes (tests of single operators)"""
+    out = [struct.pack("<IQI", lane_width, memory_size, len(ops))]
+    for name, args in ops:
+        nb = name.encode()
+        out.append(struct.pack("<H", len(nb)) + nb + struct.pack("<B", len(args)))
+        for size, is_in, lanes, elem in args:
+            out.append(struct.pack("<IBBB", size, is_in, lanes, elem))
+    code = []
+    for oi, addrs in instructions:
+        code += [oi] + list(addrs)
+    out.append(struct.pack("<QQ", len(instructions), len(code)))
+    out.append(np.asarray(code, dtype="<u8").tobytes())
+    for ports in (inputs, parameters, outputs, constants):
+        out.append(struct.pack("<I", len(ports)))
+        for q in ports:
+            out.append(struct.pack("<QQIBB", q.address, q.offset, q.size, q.lanes, q.elem))
+    out.append(struct.pack("<I", 0))  # goals
+    out.append(struct.pack("<Q", len(const_data)) + const_data)
+    return b"".join(out)
+
+
 def loads(data: bytes) -> Bundle:
     r = _Reader(data)
     if bytes(r.take(8)) != b"TRXB0001":

@@ -254,9 +254,30 @@ int emu_output(const emu_program *p, emu_memory *m, void *packed, uint64_t bytes
 
 // Walks the W streams level by level, the warps of a level one after the other and the
 // 32 threads of a warp in turn -- any valid schedule must give the same answer.
+static unsigned long long g_emu_seed = 0x9E3779B97F4A7C15ull, g_emu_epoch = 0;
+void emu_set_random_seed(unsigned long long seed) {
+  g_emu_seed = seed;
+  g_emu_epoch = 0;
+}
+// known-answer access to the generator of the in-tape random operators (csrc/vm_exec.cuh)
+void emu_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+  const uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+  uint32_t o[4];
+  trxvm::philox4x32_10(c, k, o);
+  for (int i = 0; i < 4; i++) out[i] = o[i];
+}
+
 int emu_execute(const emu_program *p, emu_memory *m) {
   m->ensure(p->low.memory_size);
   const auto &low = p->low;
+  if (low.draws_random) {
+    trxvm::RngState &st = trxvm::rngHostState();
+    st.seed = g_emu_seed;
+    st.epoch = ++g_emu_epoch;
+    st.base = m->mem.data();
+    st.tile_stride = m->tile_stride;
+    st.lane_base = 0;
+  }
   for (uint64_t t = 0; t < m->n_tiles; t++) {
     double *mem = m->mem.data() + t * m->tile_stride;
     for (size_t i = 0; i < low.const_idx.size(); i++) std::memcpy(mem + low.const_idx[i], &low.const_bits[i], 8);
