@@ -35,7 +35,12 @@ namespace tractor {
 
 class CudaEngine : public Engine {
   int _device = 0;
-  uint64_t _lanes = 8;  // rollouts per Memory; 8 = one Batch<double,8> image, byte-compatible buffers
+  // rollouts per Memory.  8 = one Batch<double,8> image: every Buffer is byte-identical to the reference's, so
+  // solvers, inputVector / outputVector and the tests work unchanged.  A multiple of 8 runs that many lane tiles per
+  // launch; Buffers handed to input() / parameterize() / output() are then the wide packed layout of
+  // include/trx_b200.h (port order kept, lane-typed ports [component][lanes], scalar-typed ports once; scalar
+  // gradients of reverse programs summed over the tiles) -- the form the objective-level calls use.
+  uint64_t _lanes = 8;
 
   static void check(trx_status s) {
     if (s != TRX_OK) throw std::runtime_error(std::string("CudaEngine: ") + trx_last_error());
@@ -64,6 +69,7 @@ class CudaEngine : public Engine {
 
   class ExecutableImpl : public Executable {
     int _device;
+    uint64_t _lanes;
     trx_program *_program = nullptr;
 
     template <class Ports> static std::vector<trx_port_desc> ports(const Ports &src) {
@@ -143,22 +149,25 @@ class CudaEngine : public Engine {
       check(trx_parameterize(_program, mem(memory), data.data(), data.size(), nullptr));
     }
     void _output(const std::shared_ptr<const Memory> &memory, Buffer &output) const override {
-      output.resize(outputBufferSize());
+      uint64_t bytes = outputBufferSize();  // 8 lanes: the reference's packed size
+      if (_lanes != 8) check(trx_program_buffer_bytes(_program, TRX_BUF_OUTPUT, _lanes, &bytes));
+      output.resize(bytes);
       auto *m = static_cast<const MemoryImpl *>(memory.get())->handle;
       check(trx_output(_program, m, output.data(), output.size(), nullptr));
     }
 
    public:
-    explicit ExecutableImpl(int device) : _device(device) {}
+    ExecutableImpl(int device, uint64_t lanes) : _device(device), _lanes(lanes) {}
     ~ExecutableImpl() override { trx_program_destroy(_program); }
   };
 
  public:
-  explicit CudaEngine(int device = 0) : _device(device) {
+  explicit CudaEngine(int device = 0, uint64_t lanes = 8) : _device(device), _lanes(lanes) {
     if (trx_device_count() <= 0) throw std::runtime_error("CudaEngine: no CUDA device (there is no CPU fallback)");
+    if (lanes == 0 || lanes % 8) throw std::runtime_error("CudaEngine: lanes must be a positive multiple of 8");
   }
   std::shared_ptr<Memory> createMemory() override { return std::make_shared<MemoryImpl>(_lanes, _device); }
-  std::shared_ptr<Executable> createExecutable() override { return std::make_shared<ExecutableImpl>(_device); }
+  std::shared_ptr<Executable> createExecutable() override { return std::make_shared<ExecutableImpl>(_device, _lanes); }
 };
 
 }  // namespace tractor

@@ -19,7 +19,8 @@ for a in sys.argv[4:]:
     opts[k] = v
 engine = pkg.CudaEngine(0)
 t0 = time.time()
-obj = pkg.RolloutObjective(engine, lanes, frames=frames, **opts)
+max_bytes = int(float(os.environ.get("ROLLOUT_MAX_GB", 0)) * 1e9)
+obj = pkg.RolloutObjective(engine, lanes, max_device_bytes=max_bytes, frames=frames, **opts)
 print("create %.2fs" % (time.time() - t0), {k: obj.info(k) for k in
       ("n_x", "grid", "rollouts_per_cta", "shared_bytes", "tiles_per_warp", "device_bytes", "n_chunks",
        "checkpoint_bytes_per_unit", "rows_per_frame", "n_joints", "n_levels")})
@@ -45,6 +46,13 @@ out = d_out.cpu().numpy()
 print("frames %d lanes %d: %.3f ms per evaluation, %.2f M timestep*rollouts/s, loss %.10g |g| %.6g" %
       (frames, lanes, ms, frames * lanes / ms / 1e3, out[0], np.linalg.norm(out[1:])))
 
+if os.environ.get("ROLLOUT_JSON"):
+    import json
+    with open(os.environ["ROLLOUT_JSON"], "a") as f:
+        f.write(json.dumps({"options": opts, "frames": frames, "rollouts": lanes, "ms_per_evaluation": ms,
+                            "timestep_rollouts_per_s": frames * lanes / ms * 1e3, "loss": float(out[0]),
+                            "n_chunks": obj.info("n_chunks"), "device_bytes": obj.info("device_bytes"),
+                            "checkpoint_bytes_per_unit": obj.info("checkpoint_bytes_per_unit")}) + "\n")
 lib = pkg._native.lib()
 if hasattr(lib, "trx_rollout_profile_dump"):
     import ctypes
