@@ -198,7 +198,14 @@ enum {
   /* keep every operand copy of x_prep (default: where a prepare rule only copies an operand, the adjoint reads the
    * forward slot instead and the copy is dropped, csrc/trx_direct.h).  Needed when a tangent program is attached
    * (trx_objective_attach_fprop): the forward_* rules read the saved operands as well. */
-  TRX_OBJECTIVE_KEEP_PREP_STATE = 8
+  TRX_OBJECTIVE_KEEP_PREP_STATE = 8,
+  /* re-rolled objectives: what a frame's checkpoint holds beyond the carried state.  Default: everything the
+   * adjoint reads (link poses, policy values, contact points), so the adjoint sweep recomputes nothing.
+   * _POLICY: the policy layers' values only (kinematics and contacts are recomputed); _STATE: the carried state
+   * only (the whole frame is recomputed, least HBM traffic).  Results are identical; DESIGN.md section 3 has the
+   * traffic / time of each. */
+  TRX_OBJECTIVE_CHECKPOINT_STATE = 16,
+  TRX_OBJECTIVE_CHECKPOINT_POLICY = 32
 };
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,

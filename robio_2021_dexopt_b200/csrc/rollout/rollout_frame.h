@@ -202,6 +202,16 @@ RL_HD void phaseSim(const Ctx &c, int lane) {
     st4(s + H[R_LQ] + k * 4, qmul(ld4(jd + JD_ORIGIN + 3), qangleaxis(q, ld3(jd + JD_AXIS))));
   }
 }
+// what is left of the simulator step when the adjoint sweep takes a frame's values from its checkpoint instead of
+// recomputing them: the joints advance, and the body state the frame started from is the carried one
+RL_HD void phaseAdvance(const Ctx &c, int lane) {
+  const int32_t *H = c.H;
+  const double dt = dconst(c)[DC_DT];
+  double *s = c.s;
+  for (int ci = lane; ci < H[H_NQ]; ci += 32) s[H[R_Q] + ci] += s[H[R_CMD] + ci] * dt;
+  if (lane == 31)
+    for (int e = 0; e < B_COUNT; e++) s[H[R_BODY0] + e] = s[H[R_BODY] + e];
+}
 // simulator step, body (one lane per rollout): integrates the dynamic body and poses the object link
 RL_HD void phaseBody(const Ctx &c) {
   const int32_t *H = c.H;

@@ -535,20 +535,27 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
   take(R_CMD, nq);
   take(R_BODY, B_COUNT);
   take(R_PREV, n_track * 7);
-  take(R_POSE, nj * 7);
+  // fields that bulk copies restore from a checkpoint (trx_rollout.cu) start on 16-byte boundaries and own an
+  // even number of doubles, so that a copy rounded up to 16 bytes stays inside its field
+  auto takeEven = [&](int key, int n) {
+    off = padTo(off, 2);
+    I[key] = off;
+    off += padTo(n, 2);
+  };
+  takeEven(R_POSE, nj * 7);
   take(R_LQ, nj * 4);
   take(R_GPOSE, nj * 6);
   take(R_GC, nj * 6);
-  take(R_VEL, std::max(nq, 1));
+  takeEven(R_VEL, std::max(nq, 1));
   take(R_GQ, nq + 1);
   take(R_GCMD, nq);
   take(R_GBODY, GB_COUNT);
-  take(R_CG, 3);
+  takeEven(R_CG, 3);
   take(R_GCG, 3);
   take(R_FIRST, 7);
   take(R_GFIRST, 6);
   take(R_GPREV, n_track * 6);
-  take(R_EE, n_ee * EE_STRIDE);
+  takeEven(R_EE, n_ee * EE_STRIDE);
   take(R_GOBJ, n_ee * 6);
   take(R_GPREVOBJ, n_ee * 6);
   take(R_BODY0, B_COUNT);

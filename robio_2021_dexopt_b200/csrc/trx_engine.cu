@@ -1884,7 +1884,8 @@ trx_status trx_objective_create_rollout(const char *options, uint64_t lanes, uin
   o->device = device;
   o->lanes = lanes;
   std::string err;
-  trx_status s = trxRolloutCreate(options, lanes, max_device_bytes, device, o->scalar_rows, &o->rollout, err);
+  const int checkpoint_mode = (flags & TRX_OBJECTIVE_CHECKPOINT_STATE) ? 0 : (flags & TRX_OBJECTIVE_CHECKPOINT_POLICY) ? 1 : 2;
+  trx_status s = trxRolloutCreate(options, lanes, max_device_bytes, device, o->scalar_rows, checkpoint_mode, &o->rollout, err);
   if (s != TRX_OK) return fail(s, err);
   o->n_x = trxRolloutInfo(o->rollout, "n_x");
   o->param_elems = trxRolloutInfo(o->rollout, "parameter_elems");

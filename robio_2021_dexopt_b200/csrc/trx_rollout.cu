@@ -58,6 +58,7 @@ struct KArgs {
   int ni, nd, nx;
   int frames, n_groups, want_grad, accumulate;
   int ckpt_doubles;  // doubles per (rollout, frame) checkpoint
+  int ckpt_mode;     // what a checkpoint holds beyond the carried state: 0 nothing, 1 the policy values, 2 everything the adjoint reads
   // shared-memory layout, in doubles
   int o_D, o_I, o_W1, o_B1, o_W2, o_B2, s_W1, s_W2, r_W1, r_W2;
   int o_X, o_H, o_A, o_O, o_GX, o_GH, o_GO, s_X, s_H, s_O;
@@ -159,6 +160,12 @@ __device__ __forceinline__ void cpAsync8(double *dst_shared, const double *src_g
                : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (both ends 16-byte aligned)
+__device__ __forceinline__ void cpAsync16(double *dst_shared, const double *src_global) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global)
+               : "memory");
+}
+
 constexpr int kHelperWarps = 8;            // helper warps of a CTA:
 constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one body warp
 
@@ -234,8 +241,57 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
   // kinematics and contacts only
   const int T = a.frames, CK = H[H_CKPT];
   const int CKX = a.ckpt_doubles;  // stride
+  const int mode = a.ckpt_mode;
+  // offsets of the optional parts inside a checkpoint
+  // (every segment starts on a 16-byte boundary and is an even number of doubles: bulk copies move them whole)
+  const int ev = 1;  // round up to even
+  const int CKP = (CK + ev) & ~ev, seg_h = (n_hid + ev) & ~ev, seg_o = (n_out + ev) & ~ev, seg_v = (H[H_NQ] + ev) & ~ev;
+  const int seg_pose = (H[H_NJ] * 7 + ev) & ~ev, seg_x = (n_in + ev) & ~ev, seg_ee = H[H_NEE] * 12;
+  const int CK_POLICY = CKP, CK_FULL = CKP + 2 * seg_h + seg_o + seg_v;
+  const int CK_X = CK_FULL + seg_pose, CK_EE = CK_X + seg_x, CK_CG = CK_EE + seg_ee;
   const int n_steps = a.want_grad ? 2 * T : T;
   double *part = a.partial + (size_t)blockIdx.x * (1 + a.nx);
+
+  // Full checkpoints (mode 2): the adjoint sweep recomputes nothing.  A frame's checkpoint -- carried state, policy
+  // values, link poses, policy input, contact points and velocities, body centre -- comes back with 16-byte
+  // asynchronous copies into the places the forward sweep had it in, each part as soon as the adjoint of the frame
+  // before has read that place for the last time, so that the copies fly while that adjoint is still running:
+  //   part 1 (after barrier C): policy outputs, commands, contact points / velocities, body centre
+  //   part 2 (after D): hidden pre-activations and activations     part 4 (after E): policy input
+  //   part 8 (top of the frame's own step, main warps only): carried state and link poses, first read by the
+  //          second contact phase
+  // thread = (rollout t & 7, 16-byte unit t >> 3); one cp.async group per call.
+  auto fetchCheckpoint = [&](int grp, int f, int parts, int n_threads) {
+    const int rr = tid & (NW - 1), u0 = tid / NW, us = n_threads / NW;
+    const int live = (int)min((long)NW, a.count - (long)grp * NW);
+    if (rr < live && f >= 0 && tid < n_threads) {
+      const double *ck = a.ckpt + (((size_t)grp * NW + rr) * T + f) * CKX;
+      double *reg = sm + a.o_region + rr * H[H_REGION];
+      auto seg = [&](double *dst, const double *src, int n) {
+        for (int u = u0; 2 * u < n; u += us) cpAsync16(dst + 2 * u, src + 2 * u);
+      };
+      if (parts & 1) {
+        seg(OS + rr * a.s_O, ck + CK_POLICY + 2 * seg_h, seg_o);
+        seg(reg + H[R_VEL], ck + CK_POLICY + 2 * seg_h + seg_o, seg_v);
+        for (int e = 0; e < H[H_NEE]; e++) seg(reg + H[R_EE] + e * EE_STRIDE, ck + CK_EE + e * 12, 12);
+        seg(reg + H[R_CG], ck + CK_CG, 4);
+      }
+      if (parts & 2) {
+        seg(HS + rr * a.s_H, ck + CK_POLICY, seg_h);
+        seg(AS + rr * a.s_H, ck + CK_POLICY + seg_h, seg_h);
+      }
+      if (parts & 4) seg(XS + rr * a.s_X, ck + CK_X, seg_x);
+      if (parts & 8) {
+        seg(reg + H[R_Q], ck, CKP);
+        seg(reg + H[R_POSE], ck + CK_FULL, seg_pose);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto fetchWait = [&](int pending) {
+    if (pending == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+  };
 
   if (warp == NW + NHD) {
     // ================================================================================ body warp
@@ -250,13 +306,36 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
       barAll();  // the group starts
       for (int step = 0; step <= n_steps; step++) {
         if ((step == T && !a.want_grad) || step == n_steps) break;
+        if (step >= T && mode == 2) {
+          if (step == T) {
+            barAll();  // F: the main warps are done with the last forward frame
+            fetchCheckpoint(grp, T - 1, 7, nt);
+          }
+          fetchWait(0);
+        }
         barAll();  // A: the frame's carried state is in place
-        if (body_lane) phaseBody(cb);
+        if (step >= T && mode == 2) {
+          // nothing to recompute: pull the next frame's checkpoints of the group towards L2 instead
+          const int f = 2 * T - 1 - step;
+          if (f > 0)
+            for (int rr = 0; rr < NW; rr++) {
+              const long local = (long)grp * NW + rr;
+              if (local >= a.count) break;
+              const double *ck = a.ckpt + ((size_t)local * T + (f - 1)) * CKX;
+              for (int line = lane; line * 16 < CKX; line += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ck + line * 16));
+            }
+        } else if (body_lane) {
+          phaseBody(cb);
+        }
         barAll();  // B
         if (step < T) continue;
+        const int f_next = 2 * T - 2 - step;  // the frame of the next step
         barAll();  // C
+        if (mode == 2) fetchCheckpoint(grp, f_next, 1, nt);
         barAll();  // D
+        if (mode == 2) fetchCheckpoint(grp, f_next, 2, nt);
         barAll();  // E: the object's pose adjoint is complete
+        if (mode == 2) fetchCheckpoint(grp, f_next, 4, nt);
         if (body_lane) bphaseBody(cb);
         barAll();  // G: the frame is done
       }
@@ -278,10 +357,19 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
       barAll();  // the group starts
       for (int step = 0; step <= n_steps; step++) {
         if ((step == T && !a.want_grad) || step == n_steps) break;
+        if (step >= T && mode == 2) {
+          if (step == T) {
+            barAll();  // F
+            fetchCheckpoint(grp, T - 1, 7, nt);
+          }
+          fetchWait(0);
+        }
         barAll();  // A
         barAll();  // B
         if (step < T) continue;
+        const int f_next = 2 * T - 2 - step;  // the frame of the next step
         barAll();  // C: output adjoint of the last layer complete
+        if (mode == 2) fetchCheckpoint(grp, f_next, 1, nt);
 #ifdef TRX_ROLLOUT_PROFILE
         long long _h0 = clock64();
 #endif
@@ -337,7 +425,9 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
 #ifdef TRX_ROLLOUT_PROFILE
         if (htid == 0) sprof[51] += clock64() - _h0;
 #endif
+        if (mode == 2) fetchCheckpoint(grp, f_next, 2, nt);
         barAll();  // E
+        if (mode == 2) fetchCheckpoint(grp, f_next, 4, nt);
         barAll();  // G: the frame is done
       }
     }
@@ -447,11 +537,14 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         c.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
         if (active) {
           bphaseInit(c, slot);
-          const double *ck = ckpt + (size_t)(T - 1) * CKX;
+          if (mode != 2) {
+            const double *ck = ckpt + (size_t)(T - 1) * CKX;
 #pragma unroll
-          for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
+            for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
+          }
         }
-        barMain<NTM>();
+        if (mode == 2) barAll();  // F: the body warp may overwrite the forward values with the checkpoint's
+        else barMain<NTM>();
       }
       if (step == n_steps) break;
 
@@ -459,80 +552,103 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
       if (!rec) {
         PH(12, if (active) phaseBeginFrame(c, slot, f, ckpt + (size_t)f * CKX));
       } else {
-        PH(13, if (active) {
+        PH(13, if (active && mode != 2) {
           phaseLoadCheckpoint(c, slot, pre);
-          // the frame's policy values travel from the checkpoint straight into the activation matrices while
-          // the kinematics are recomputed (nobody reads them before the contact phases)
-          const double *ck = ckpt + (size_t)f * CKX + CK;
-          for (int e = slot; e < n_hid; e += 32) {
-            cpAsync8(c.h + e, ck + e);
-            cpAsync8(c.a + e, ck + n_hid + e);
+          const double *ck = ckpt + (size_t)f * CKX;
+          if (mode >= 1) {
+            // the frame's policy values travel from the checkpoint straight into the activation matrices while
+            // the kinematics are recomputed (nobody reads them before the contact phases)
+            const double *cp = ck + CK_POLICY;
+            for (int e = slot; e < n_hid; e += 32) {
+              cpAsync8(c.h + e, cp + e);
+              cpAsync8(c.a + e, cp + seg_h + e);
+            }
+            for (int e = slot; e < n_out; e += 32) cpAsync8(c.out + e, cp + 2 * seg_h + e);
+            for (int e = slot; e < nq; e += 32) cpAsync8(c.s + H[R_VEL] + e, cp + 2 * seg_h + seg_o + e);
           }
-          for (int e = slot; e < n_out; e += 32) cpAsync8(c.out + e, ck + 2 * n_hid + e);
-          for (int e = slot; e < nq; e += 32) cpAsync8(c.s + H[R_VEL] + e, ck + 2 * n_hid + n_out + e);
           asm volatile("cp.async.commit_group;" ::: "memory");
         });
       }
+      if (rec && mode == 2) {
+        // carried state and link poses of this frame: nobody needs them before the second contact phase
+        PH(13, if (step == T) fetchCheckpoint(grp, f, 7, nt); fetchCheckpoint(grp, f, 8, NTM); fetchWait(1));
+      }
       barAll();  // A: the body step may start
-      if (rec && active && f > 0) {  // the next checkpoint lands while this frame is being worked on
+      if (rec && mode != 2 && active && f > 0) {  // the next checkpoint lands while this frame is being worked on
         const double *ck = ckpt + (size_t)(f - 1) * CKX;
 #pragma unroll
         for (int i = 0; i < kPre; i++) pre[i] = (slot + 32 * i < CK) ? ck[slot + 32 * i] : 0.0;
       }
-      PH(0, if (active) phaseSim(c, slot); barMain<NTM>());
-      PH(1, if (warp < live) for (int rd = 0; rd < n_round; rd++) {
-        fkRoundForward<1, DeviceWarp>(cw, rd, lane);
-        __syncwarp();
-      });
-      PH(15, barAll());  // B: link poses and the body step are complete
-      PH(2, if (active) { if (rec) phaseObserve<false>(c, slot, f, loss); else phaseObserve<true>(c, slot, f, loss); });
-      if (n_layers) {
-        // The policy layers' epilogues carry what follows them: activity / command regularisation rows and
-        // tanh (dexenv_grasp.h:137-146,186-199), so the hidden and control steps cost no phase of their own.
-        const long row_act = (long)f * rows_frame + H[H_ROW_ACT], row_cmd = (long)f * rows_frame + H[H_ROW_CMD];
-        if (rec) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        PH(3, barMain<NTM>());
-        if (!rec && n_layers == 2) {
-          PH(4, denseTiles(XS, a.s_X, sW1, a.s_W1, 1, k1, n_hid, warp, NW, lane, [=, &loss](int g, int j, double v) {
-            v += sB1[j];
-            HS[g * a.s_H + j] = v;
-            AS[g * a.s_H + j] = tanh(v);
-            if (j < n_hid && g < live) {
-              const double rr = v * w_reg;
-              loss += rr * rr;
-              if (grp_r) grp_r[(row_act + j) * a.R + g] = rr;
-            }
-          }));
+      if (rec && mode == 2) {
+        // nothing is recomputed: the joints advance (q += command * dt), the body state the frame started from is
+        // the carried one, the rest arrives from the checkpoint
+        PH(15, barAll());  // B
+      } else {
+        PH(0, if (active) phaseSim(c, slot); barMain<NTM>());
+        PH(1, if (warp < live) for (int rd = 0; rd < n_round; rd++) {
+          fkRoundForward<1, DeviceWarp>(cw, rd, lane);
+          __syncwarp();
+        });
+        PH(15, barAll());  // B: link poses and the body step are complete
+        PH(2, if (active) { if (rec) phaseObserve<false>(c, slot, f, loss); else phaseObserve<true>(c, slot, f, loss); });
+        if (n_layers) {
+          // The policy layers' epilogues carry what follows them: activity / command regularisation rows and
+          // tanh (dexenv_grasp.h:137-146,186-199), so the hidden and control steps cost no phase of their own.
+          const long row_act = (long)f * rows_frame + H[H_ROW_ACT], row_cmd = (long)f * rows_frame + H[H_ROW_CMD];
+          const bool layers_now = !rec || mode == 0;  // otherwise their values come from the checkpoint
+          const bool count = !rec;                    // residual rows count in the forward sweep only
+          if (rec) asm volatile("cp.async.wait_group 0;" ::: "memory");
           PH(3, barMain<NTM>());
-        }
-        if (!rec) {
-          const double *Xl = n_layers == 2 ? AS : XS, *Wl = n_layers == 2 ? sW2 : sW1, *Bl = n_layers == 2 ? sB2 : sB1;
-          const int sXl = n_layers == 2 ? a.s_H : a.s_X, sWl = n_layers == 2 ? a.s_W2 : a.s_W1;
-          double *vel = sm + a.o_region + H[R_VEL];
-          const int region = H[H_REGION];
-          PH(6, denseTiles(Xl, sXl, Wl, sWl, 1, n_layers == 2 ? k2 : k1, n_out, warp, NW, lane,
-                           [=, &loss](int g, int j, double v) {
-                             v += Bl[j];
-                             OS[g * a.s_O + j] = v;
-                             if (j < nq && g < NW) vel[g * region + j] = tanh(v);
-                             if (j < n_out && g < live) {
-                               const double rr = v * w_creg;
-                               loss += rr * rr;
-                               if (grp_r) grp_r[(row_cmd + j) * a.R + g] = rr;
-                             }
-                           }));
-          PH(3, barMain<NTM>());
-          if (active) {
-            double *ck = ckpt + (size_t)f * CKX + CK;
-            for (int e = slot; e < n_hid; e += 32) ck[e] = c.h[e], ck[n_hid + e] = c.a[e];
-            for (int e = slot; e < n_out; e += 32) ck[2 * n_hid + e] = c.out[e];
-            for (int e = slot; e < nq; e += 32) ck[2 * n_hid + n_out + e] = c.s[H[R_VEL] + e];
+          if (layers_now && n_layers == 2) {
+            PH(4, denseTiles(XS, a.s_X, sW1, a.s_W1, 1, k1, n_hid, warp, NW, lane, [=, &loss](int g, int j, double v) {
+              v += sB1[j];
+              HS[g * a.s_H + j] = v;
+              AS[g * a.s_H + j] = tanh(v);
+              if (count && j < n_hid && g < live) {
+                const double rr = v * w_reg;
+                loss += rr * rr;
+                if (grp_r) grp_r[(row_act + j) * a.R + g] = rr;
+              }
+            }));
+            PH(3, barMain<NTM>());
           }
-        }
-        PH(8, if (active) { if (rec) phaseContact1<false>(c, slot, f, loss); else phaseContact1<true>(c, slot, f, loss); } barMain<NTM>());
-        PH(9, if (active) phaseContact2(c, slot, f); barMain<NTM>());
-        if (!rec) {
-          PH(10, if (active) phaseContact3(c, slot, f, loss); barMain<NTM>());
+          if (layers_now) {
+            const double *Xl = n_layers == 2 ? AS : XS, *Wl = n_layers == 2 ? sW2 : sW1, *Bl = n_layers == 2 ? sB2 : sB1;
+            const int sXl = n_layers == 2 ? a.s_H : a.s_X, sWl = n_layers == 2 ? a.s_W2 : a.s_W1;
+            double *vel = sm + a.o_region + H[R_VEL];
+            const int region = H[H_REGION];
+            PH(6, denseTiles(Xl, sXl, Wl, sWl, 1, n_layers == 2 ? k2 : k1, n_out, warp, NW, lane,
+                             [=, &loss](int g, int j, double v) {
+                               v += Bl[j];
+                               OS[g * a.s_O + j] = v;
+                               if (j < nq && g < NW) vel[g * region + j] = tanh(v);
+                               if (count && j < n_out && g < live) {
+                                 const double rr = v * w_creg;
+                                 loss += rr * rr;
+                                 if (grp_r) grp_r[(row_cmd + j) * a.R + g] = rr;
+                               }
+                             }));
+            PH(3, barMain<NTM>());
+            if (!rec && mode >= 1 && active) {
+              double *cp = ckpt + (size_t)f * CKX + CK_POLICY;
+              for (int e = slot; e < seg_h; e += 32) cp[e] = e < n_hid ? c.h[e] : 0.0, cp[seg_h + e] = e < n_hid ? c.a[e] : 0.0;
+              for (int e = slot; e < seg_o; e += 32) cp[2 * seg_h + e] = e < n_out ? c.out[e] : 0.0;
+              for (int e = slot; e < seg_v; e += 32) cp[2 * seg_h + seg_o + e] = e < nq ? c.s[H[R_VEL] + e] : 0.0;
+            }
+          }
+          PH(8, if (active) { if (rec) phaseContact1<false>(c, slot, f, loss); else phaseContact1<true>(c, slot, f, loss); } barMain<NTM>());
+          PH(9, if (active) phaseContact2(c, slot, f); barMain<NTM>());
+          if (!rec) {
+            if (mode == 2 && active) {
+              double *ck = ckpt + (size_t)f * CKX;
+              const int n_pose = H[H_NJ] * 7;
+              for (int e = slot; e < seg_pose; e += 32) ck[CK_FULL + e] = e < n_pose ? c.s[H[R_POSE] + e] : 0.0;
+              for (int e = slot; e < seg_x; e += 32) ck[CK_X + e] = e < n_in ? c.x[e] : 0.0;
+              for (int e = slot; e < seg_ee; e += 32) ck[CK_EE + e] = c.s[H[R_EE] + (e / 12) * EE_STRIDE + e % 12];
+              for (int e = slot; e < 4; e += 32) ck[CK_CG + e] = e < 3 ? c.s[H[R_CG] + e] : 0.0;
+            }
+            PH(10, if (active) phaseContact3(c, slot, f, loss); barMain<NTM>());
+          }
         }
       }
       if (!rec) continue;
@@ -543,12 +659,18 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         barMain<NTM>();
       });
       if (n_layers) {
-        PH(33, if (active) bphaseContact3(c, slot, f); barMain<NTM>());
+        PH(33, if (active) bphaseContact3(c, slot, f); if (mode == 2) fetchWait(0); barMain<NTM>());
+        if (mode == 2) {
+          // the carried state has landed: the joints advance, the body state the frame started from is the carried one
+          PH(0, if (active) phaseAdvance(c, slot));
+        }
         PH(34, if (active) bphaseContact2(c, slot, f); barMain<NTM>());
         PH(35, if (active) bphaseContact1(c, slot, f); barMain<NTM>());
         PH(36, if (active) bphaseControl(c, slot, f));
       }
+      const int f_next = f - 1;
       PH(46, barAll());  // C: the helper warps take dW and db of the last layer from here
+      if (mode == 2) fetchCheckpoint(grp, f_next, 1, nt);
       if (n_layers == 2) {
         // input adjoint of the last layer, with the tanh / activity-row adjoint of the hidden layer in its epilogue
         const long row_act = (long)f * rows_frame + H[H_ROW_ACT];
@@ -565,6 +687,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
                           [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
       }
       PH(47, barAll());  // D: ... and of the first layer from here
+      if (mode == 2) fetchCheckpoint(grp, f_next, 2, nt);
       if (n_layers == 2) {
         PH(41, denseTiles(GHS, a.s_H, sW1, 1, a.s_W1, k2, n_in, warp, NW, lane,
                           [=](int g, int i, double v) { GXS[g * a.s_X + i] = v; }));
@@ -572,6 +695,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
       }
       PH(43, if (active) bphaseObserve(c, slot, f); barMain<NTM>(); if (warp < live) bphaseObjectGather(cw, lane));
       PH(48, barAll());  // E: the body adjoint may start
+      if (mode == 2) fetchCheckpoint(grp, f_next, 4, nt);
       PH(44, if (warp < live) {
         for (int rd = n_round - 1; rd >= 0; rd--) {
           fkRoundReverse<1, DeviceWarp>(cw, rd, lane);
@@ -680,7 +804,7 @@ const Variant kVariants[] = {RL_VARIANT(8, 2, 7), RL_VARIANT(8, 7, 13), RL_VARIA
 }  // namespace
 
 trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_device_bytes, int device,
-                            bool scalar_rows, trx_rollout **out, std::string &err) {
+                            bool scalar_rows, int checkpoint_mode, trx_rollout **out, std::string &err) {
   *out = nullptr;
   std::unique_ptr<trx_rollout, void (*)(trx_rollout *)> ro(new trx_rollout(), trxRolloutDestroy);
   try {
@@ -784,8 +908,15 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
 
   // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
-  a.ckpt_doubles = I[H_CKPT] + 2 * n_hid + n_out + I[H_NQ];
-  a.ckpt_doubles += a.ckpt_doubles & 1;  // 16-byte rows
+  // what a checkpoint holds beyond the carried state: the more, the less the adjoint sweep
+  // recomputes and the more crosses HBM.  TRX_ROLLOUT_CHECKPOINT = 0 | 1 | 2 overrides the default.
+  a.ckpt_mode = checkpoint_mode;
+  if (const char *w = getenv("TRX_ROLLOUT_CHECKPOINT")) a.ckpt_mode = std::max(0, std::min(2, atoi(w)));
+  auto even = [](int n) { return (n + 1) & ~1; };
+  a.ckpt_doubles = even(I[H_CKPT]);
+  if (a.ckpt_mode >= 1) a.ckpt_doubles += 2 * even(n_hid) + even(n_out) + even(I[H_NQ]);
+  if (a.ckpt_mode == 2) a.ckpt_doubles += even(I[H_NJ] * 7) + even(n_in) + I[H_NEE] * 12 + 4;
+  a.ckpt_doubles = (a.ckpt_doubles + 15) / 16 * 16;  // whole 128-byte lines
   const uint64_t ck_bytes_per_rollout = (uint64_t)a.frames * a.ckpt_doubles * sizeof(double);
   uint64_t chunk = lanes;
   if (max_device_bytes && chunk * ck_bytes_per_rollout > max_device_bytes)
@@ -839,6 +970,7 @@ uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key) {
   if (k == "rows_per_frame") return I[H_ROWS_FRAME];
   if (k == "checkpoint_bytes_per_unit") return (uint64_t)ro->args.ckpt_doubles * 8;
   if (k == "carried_state_bytes_per_unit") return (uint64_t)I[H_CKPT] * 8;
+  if (k == "checkpoint_mode") return (uint64_t)ro->args.ckpt_mode;
   if (k == "rollouts_per_cta") return ro->nw;
   if (k == "grid") return ro->grid;
   if (k == "shared_bytes") return ro->smem_bytes;

@@ -11,7 +11,7 @@
 struct trx_rollout;
 
 trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_device_bytes, int device,
-                            bool scalar_rows, trx_rollout **out, std::string &err);
+                            bool scalar_rows, int checkpoint_mode, trx_rollout **out, std::string &err);
 void trxRolloutDestroy(trx_rollout *ro);
 // ~0 for an unknown key
 uint64_t trxRolloutInfo(const trx_rollout *ro, const char *key);

@@ -170,7 +170,9 @@ def test_rollout_full_size_properties(cuda_engine):
     assert np.isfinite(l_a) and np.all(np.isfinite(g_a))
     # device memory is rollouts x frames x checkpoint (carried state + the frame's policy values), nothing else
     assert full.info("device_bytes") < 1024 * 256 * full.info("checkpoint_bytes_per_unit") + 20e6
-    assert full.info("checkpoint_bytes_per_unit") <= 8 * (120 + 2 * 64 + 83 + 29 + 1)
+    # default checkpoint: carried state (120 doubles) + policy values (240) + link poses, policy input, contact
+    # points and velocities, body centre (382), in whole 128-byte lines
+    assert full.info("checkpoint_bytes_per_unit") <= 8 * (120 + 240 + 382 + 15)
     half0 = _objective(cuda_engine, opts, lanes // 2)
     half1 = _objective(cuda_engine, opts, lanes // 2, scalar_rows=False)
     half0.parameterize(pw[:, :lanes // 2].copy())
