@@ -395,3 +395,46 @@ def test_least_squares_iterates_match_reference(cuda_engine, golden):
         err = np.max(np.abs(solver.scatter() - want_x[k])) / np.max(np.abs(want_x[k]))
         assert err <= 1e-7, (k, err)
     assert solver.loss() < float(ref.arrays["sq/loss"][0])
+
+
+# ------------------------------------------------------------------ properties of the derived programs on the device
+
+@pytest.mark.gpu
+def test_accu_program_on_gpu(cuda_engine, golden):
+    """the derived `accu` program (x (+) delta, tractor/src/core/gradients.cpp:364-406; SolverBase::accumulate,
+    solvers/base.h:158-165) executed as an executable: scalar inputs accumulate by plain addition"""
+    import robio_2021_dexopt_b200 as pkg
+    mine = pkg.build_dexsyn(frames=2, hidden=4, extra_fixed=2, programs="prog,accu")
+    accu = cuda_engine.compile(mine.programs["accu"])
+    mem = cuda_engine.createMemory(8)
+    x = mine.arrays["x"]
+    rng = np.random.default_rng(17)
+    delta = rng.standard_normal(x.size)
+    out = accu.run(np.concatenate([x, delta]), mem)
+    assert np.array_equal(out, x + delta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fuse_dense", [0, 1])
+def test_tangent_and_adjoint_sweeps_are_adjoint(cuda_engine, golden, fuse_dense):
+    """<J dx, v> = <dx, J^T v> for random dx and v (the property the reference's own tests check per operator,
+    tractor/src/test/test.cpp:629-645), on the whole objective tape over two lane tiles, on the device"""
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("dexsyn_small.trxb.xz")
+    mine = pkg.build_dexsyn(frames=3, hidden=4, extra_fixed=4, fuse_dense=fuse_dense)
+    views = {n: mine.view(n) for n in ("prog", "fprop", "bprop")}
+    x_prog, x_prep, x_fprop, x_bprop = (cuda_engine.compile(mine.programs[n]) for n in ("prog", "prep", "fprop", "bprop"))
+    lanes = 8  # one tile: stand-alone executables keep the reference's semantics of scalar rows exactly
+    mem = cuda_engine.createMemory(lanes)
+    params = parity.tile_arrays(ref, "params")[0]
+    x_prog.parameterize(params, mem)
+    r = x_prog.run(ref.arrays["x"], mem)
+    x_prep.execute(mem)
+    rng = np.random.default_rng(23)
+    dx = rng.standard_normal(ref.arrays["x"].size)
+    v = rng.standard_normal(r.size)
+    jdx = x_fprop.run(dx, mem)
+    jtv = x_bprop.run(v, mem)
+    lhs, rhs = float(jdx @ v), float(dx @ jtv)
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
