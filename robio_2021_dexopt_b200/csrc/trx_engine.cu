@@ -24,7 +24,10 @@
 
 #include "../../include/trx_b200.h"
 #include "trx_lower.h"
-#include "trx_fuse.h"
+#include "trx_combine.h"
+#ifdef TRX_WITH_EXPERIMENTS
+#include "trx_fuse.h"  // chain scheduling with on-chip slot rings: measured slower, not in the product library
+#endif
 #include "trx_direct.h"
 #include "vm_exec.cuh"
 #include "trx_comm.h"
@@ -1190,6 +1193,9 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
     uint32_t W = p->low.n_warps;
     size_t smem = (size_t)W * p->low.ring_doubles * sizeof(double);
     if (p->low.ring_doubles) {
+#ifndef TRX_WITH_EXPERIMENTS
+      return fail(TRX_ERR_UNSUPPORTED, "on-chip slot rings are an experiment that is not built into this library");
+#else
       if (firstUseOnDevice(m->device, 0))
         TRX_CUDA(cudaFuncSetAttribute(trx_vm_kernel<16, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       if (p->low.cta_ring) smem = (size_t)p->low.ring_doubles * sizeof(double);
@@ -1197,6 +1203,7 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
           p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, p->low.ring_doubles, g_trace,
           p->low.cta_ring ? p->d_pool : nullptr, p->low.pool_offset_doubles, (uint32_t)p->low.pool_values.size(),
           p->low.page_words);
+#endif
     } else if (p->low.page_words == 512 && !p->low.global_pool && staged_streams()) {
       // the product path: stream pages staged in shared memory
       constexpr int kPages = 4;
@@ -1319,6 +1326,7 @@ struct trx_objective {
 
 extern "C" {
 
+#ifdef TRX_WITH_EXPERIMENTS
 // Fused lowering of the objective's two sweeps (trx_fuse.h)
 static trx_status lowerObjectiveFused(const trxfile::Program &prog, const trxfile::Program &prep,
                                       const trxfile::Program &bprop, std::unique_ptr<trx_program> &fwd,
@@ -1337,6 +1345,8 @@ static trx_status lowerObjectiveFused(const trxfile::Program &prog, const trxfil
   return TRX_OK;
 }
 
+#endif
+
 trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const void *prep_blob, size_t prep_bytes,
                                 const void *bprop_blob, size_t bprop_bytes, uint64_t lanes, uint64_t max_device_bytes,
                                 int device, int flags, trx_objective **out) {
@@ -1346,6 +1356,11 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
   // every early return below releases what has been built so far
   std::unique_ptr<trx_objective, void (*)(trx_objective *)> o(new trx_objective(), trx_objective_destroy);
   o->fused = (flags & TRX_OBJECTIVE_FUSED) != 0;
+#ifndef TRX_WITH_EXPERIMENTS
+  if (o->fused)
+    return fail(TRX_ERR_UNSUPPORTED, "TRX_OBJECTIVE_FUSED: the experimental ring lowering is not built into this library "
+                                     "(-DTRX_WITH_EXPERIMENTS)");
+#endif
   o->scalar_rows = (flags & TRX_OBJECTIVE_NO_SCALAR_ROWS) == 0;
   {
     trxfile::Program p_prog, p_prep, p_bprop;
@@ -1365,6 +1380,7 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
     }
     trx_status s;
     trx_program *raw = nullptr;
+#ifdef TRX_WITH_EXPERIMENTS
     if (o->fused) {
       std::unique_ptr<trx_program> fwd(new trx_program()), adj(new trx_program());
       if ((s = lowerObjectiveFused(p_prog, p_prep, p_bprop, fwd, adj)) != TRX_OK) return s;
@@ -1373,7 +1389,9 @@ trx_status trx_objective_create(const void *prog_blob, size_t prog_bytes, const 
       if ((s = finishProgram(adj, device, TRX_SCALAR_REDUCE, TRX_SCALAR_REDUCE, &raw)) != TRX_OK) return s;
       o->bprop = raw;
       o->prep = nullptr;
-    } else if (flags & TRX_OBJECTIVE_SEPARATE) {
+    } else
+#endif
+    if (flags & TRX_OBJECTIVE_SEPARATE) {
       if ((s = createFromFile(p_prog, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;
       o->prog = raw;
       if ((s = createFromFile(p_prep, device, TRX_SCALAR_AUTO, TRX_SCALAR_AUTO, &raw)) != TRX_OK) return s;

@@ -138,7 +138,7 @@ def test_many_tiles_replicate_the_reference_tile(cuda_engine, golden):
 @pytest.mark.gpu
 @pytest.mark.parametrize("fixture", ["fkchain24.trxb", "dexsyn_small.trxb.xz", "dexsyn_dropout_outer2.trxb.xz"])
 @pytest.mark.parametrize("max_bytes", [0, 1])
-@pytest.mark.parametrize("fused,separate", [(True, False), (False, False), (False, True)])
+@pytest.mark.parametrize("fused,separate", [(False, False), (False, True)])
 def test_objective_matches_reference(cuda_engine, golden, fixture, max_bytes, fused, separate):
     """trx_objective_evaluate (one C-ABI call per solver step) against the reference's loss and J^T r;
     max_bytes=1 forces one lane tile per chunk, i.e. the chunked walk over rollouts"""
@@ -293,7 +293,7 @@ def test_cuda_engine_against_the_oracle_restatement_on_fresh_inputs(cuda_engine,
         xs["prep"].execute(mem)
         g_want = g_want + xs["bprop"].run(rr, mem)
     import robio_2021_dexopt_b200 as pkg
-    for fused in (False, True):
+    for fused in (False,):  # the ring lowering (trx_fuse.h) is an experiment outside the product library
         obj = pkg.Objective(cuda_engine, bundle, lanes=8 * tiles, fused=fused)
         obj.parameterize(trxfile.tiles_to_wide(prog.parameters, params))
         loss, g = obj.evaluate(x)
