@@ -166,6 +166,38 @@ trx_status trx_output_device(const trx_program *p, trx_memory *m, void *d_packed
  * instruction) -- Philox4x32-10 -- so a run can be repeated: setting the seed restarts the execute counter. */
 void trx_set_random_seed(uint64_t seed);
 
+/* Collision shapes for the operators collision_axes and collision_project_2 (dexopt/src/ops.h:208-252,288-375).
+ * The reference's tape carries host pointers to CollisionShape / ShapeCollisionPair objects
+ * (tractor/include/tractor/collision/shape.h:51-347, collision/query.h:123-152) as uint64 constants and calls Bullet
+ * GJK/EPA on the host per lane; here the same constants are handles into a process-wide shape table that the library
+ * mirrors to every device it runs on, and the queries run per lane inside the kernel (csrc/collision/trx_collide.h).
+ *   kind TRX_SHAPE_SPHERE:     center, radius                          (shape.h:51-63)
+ *   kind TRX_SHAPE_CYLINDER:   radius, length, axis z, centred         (shape.h:139-171)
+ *   kind TRX_SHAPE_POLYHEDRON: points (support mapping), planes (nx ny nz offset, inside <= 0; project());
+ *                              center = mean of the points             (shape.h:196-222,327-346)
+ * A pair names the two shapes of one collision_axes instruction.  Handles stay valid until trx_collision_clear. */
+enum { TRX_SHAPE_SPHERE = 1, TRX_SHAPE_CYLINDER = 2, TRX_SHAPE_POLYHEDRON = 3 };
+typedef struct trx_shape_desc {
+  int kind;
+  double center[3]; /* sphere; ignored for polyhedra (computed) and cylinders (0) */
+  double radius, length;
+  uint32_t n_points, n_planes;
+  const double *points; /* 3 * n_points */
+  const double *planes; /* 4 * n_planes */
+} trx_shape_desc;
+trx_status trx_collision_shape_create(const trx_shape_desc *desc, uint64_t *handle);
+trx_status trx_collision_pair_create(uint64_t shape_a, uint64_t shape_b, uint64_t *handle);
+trx_status trx_collision_shape_center(uint64_t shape, double *center3);
+void trx_collision_clear(void);
+/* copy of the table (doubles; records as csrc/collision/trx_collide.h lays them out): *count = its length,
+ * up to `capacity` doubles are written to `out` (out may be NULL to ask for the length) */
+trx_status trx_collision_table(double *out, uint64_t capacity, uint64_t *count);
+/* the two queries themselves on the device, one thread per query (tests, and callers outside a tape):
+ * poses = n x 14 doubles (pose a, pose b as translation xyz + quaternion xyzw), out = n x 10 (a, b, normal, distance);
+ * points = n x 3, out = n x 4 (normal, distance).  Host pointers. */
+trx_status trx_collision_query_pairs(uint64_t pair, const double *poses, uint64_t n, double *out, int device);
+trx_status trx_collision_project_points(uint64_t shape, const double *points, uint64_t n, double *out, int device);
+
 /* number of kernels this library has launched since load (for launch accounting) */
 uint64_t trx_kernel_launch_count(void);
 

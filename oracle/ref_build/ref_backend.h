@@ -12,6 +12,8 @@
 namespace refc {
 
 template <class Lane> struct RefBackend {
+  // collision_axes / collision_project_2 call Bullet in the reference (src/collision/query.cpp): not buildable here
+  static constexpr bool kHasCollisionOps = false;
   typedef Lane LaneValue;  // tractor::Batch8d
   typedef tractor::Var<Lane> S;
   typedef tractor::Var<double> W;

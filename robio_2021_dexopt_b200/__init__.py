@@ -8,5 +8,6 @@ Only what the path needs lives here:
 from .engine import CudaEngine, Executable, Memory, kernel_launch_count  # noqa: F401
 from ._native import TrxError  # noqa: F401
 from . import trxfile  # noqa: F401
+from . import collision  # noqa: F401
 from .builder import build_dexsyn  # noqa: F401
 from .solver import GradientDescentSolver, LeastSquaresSolver, Objective, RolloutObjective  # noqa: F401

@@ -54,6 +54,13 @@ def lib() -> ctypes.CDLL:
         getattr(L, name).argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint64, c.c_void_p]
     L.trx_execute.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     L.trx_memory_peek.argtypes = [c.c_void_p, c.c_uint64, c.c_uint64, c.c_void_p, c.c_uint64]
+    L.trx_collision_shape_create.argtypes = [c.c_void_p, c.POINTER(c.c_uint64)]
+    L.trx_collision_pair_create.argtypes = [c.c_uint64, c.c_uint64, c.POINTER(c.c_uint64)]
+    L.trx_collision_shape_center.argtypes = [c.c_uint64, c.POINTER(c.c_double)]
+    L.trx_collision_clear.restype = None
+    L.trx_collision_table.argtypes = [c.c_void_p, c.c_uint64, c.POINTER(c.c_uint64)]
+    L.trx_collision_query_pairs.argtypes = [c.c_uint64, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
+    L.trx_collision_project_points.argtypes = [c.c_uint64, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
     L.trx_objective_create.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t,
                                        c.c_uint64, c.c_uint64, c.c_int, c.c_int, c.POINTER(c.c_void_p)]
     L.trx_objective_destroy.argtypes = [c.c_void_p]

@@ -21,12 +21,16 @@
 // so the oracle and the product are fed the same problem, and only the
 // execution engines differ.
 //
-// Deliberate omissions (parity unpinned without Bullet/Eigen):
-// collision_axes penalties (dexlearn.h:66-131) and the collision_project_2
-// friction-cone normals (dexlearn.h:324-362).  Random draws (object start pose,
-// dropout masks) enter as per-lane parameters instead of in-tape RNG ops (H4).
+// Collision penalties (collision_axes, dexlearn.h:66-131) and friction-cone penalties
+// (collision_project_2 normals, dexlearn.h:219-233,324-362) are recorded when the model
+// carries registered shapes (Model::collision_pairs, Model::friction_cones) and the
+// backend has the two operators -- the product recorder has, the reference-API recorder
+// in this image has not (its operators call Bullet: parity unpinned).
+// Random draws (object start pose, dropout masks) enter as per-lane parameters instead
+// of in-tape RNG ops (H4).
 #pragma once
 #include <cmath>
+#include <stdexcept>
 #include <vector>
 
 #include "dexsyn_model.h"
@@ -249,7 +253,64 @@ template <class B> struct Assembler {
     }
   }
 
-  // dexlearn.h:235-391 (friction-cone part omitted, see header)
+  // dexlearn.h:66-131: one closest-point query per shape pair; the witnesses are re-attached to their links
+  // (local_a, local_b are constants for the derivative, the link poses are not)
+  void collisionPenalties() {
+    if constexpr (B::kHasCollisionOps) collisionPenaltiesImpl();
+    else if (!model.collision_pairs.empty()) throw std::runtime_error("this recorder has no collision operators");
+  }
+  void collisionPenaltiesImpl() {
+    for (auto &cp : model.collision_pairs) {
+      const P &pose_a = link_pose[cp.link_a], &pose_b = link_pose[cp.link_b];
+      V3 point_a, point_b, axis, local_a, local_b;
+      b.collisionAxes(pose_a, pose_b, cp.handle, point_a, point_b, axis, local_a, local_b);
+      point_a = b.pmulv(pose_a, local_a);
+      point_b = b.pmulv(pose_b, local_b);
+      S distance = b.dot(axis, b.vsub(point_a, point_b));
+      if (env.collision_penalty) b.goal(b.mul(b.relu(b.neg(distance)), b.cs(env.collision_penalty)));
+      if (env.collision_avoidance_weight)
+        b.goal(b.mul(b.relu(b.add(b.neg(distance), b.cs(env.collision_avoidance_distance))),
+                     b.cs(env.collision_avoidance_weight)));
+      if (env.slip_avoidance_weight) {
+        V3 p_center = b.vmuls(b.vadd(point_a, point_b), b.cs(0.5));
+        V3 v1 = velocity(cp.link_a, p_center);
+        V3 v2 = velocity(cp.link_b, p_center);
+        b.goalV(b.vmuls(b.vsub(v2, v1), b.mul(b.relu(b.add(b.neg(distance), b.cs(env.slip_avoidance_distance))),
+                                              b.cs(env.slip_avoidance_weight))));
+      }
+    }
+  }
+
+  // dexlearn.h:219-233
+  void frictionConePenalties(const V3 &contact_force, const V3 &contact_normal, const S &weight) {
+    for (int sign : {-1, +1})
+      for (int axis = 0; axis < 3; axis++) {
+        V3 v = b.pack(b.cs(axis == 0), b.cs(axis == 1), b.cs(axis == 2));
+        V3 n = b.vadd(contact_normal, b.cross(contact_normal, b.vmuls(v, b.cs(sign * 0.5))));
+        b.goal(b.mul(b.relu(b.neg(b.dot(n, contact_force))), weight));
+      }
+  }
+
+  // dexlearn.h:324-362
+  void frictionCones(int obj_link, int ee_link, const Shape &obj_shape, const Shape &ee_shape, const V3 &c1, const V3 &c2,
+                     const V3 &force) {
+    {
+      V3 normal;
+      S distance;
+      b.collisionProject(b.pmulv(pinv(link_pose[obj_link]), c2), obj_shape.handle, normal, distance);
+      normal = b.qmulv(b.porientation(link_pose[obj_link]), normal);
+      if (env.friction_cone_penalty) frictionConePenalties(force, normal, b.cs(env.friction_cone_penalty));
+    }
+    {
+      V3 normal;
+      S distance;
+      b.collisionProject(b.pmulv(pinv(link_pose[ee_link]), c1), ee_shape.handle, normal, distance);
+      normal = b.qmulv(b.porientation(link_pose[ee_link]), normal);
+      if (env.friction_cone_penalty) frictionConePenalties(b.vneg(force), normal, b.cs(env.friction_cone_penalty));
+    }
+  }
+
+  // dexlearn.h:235-391
   void evaluateContact(int ee_index, const std::vector<S> &cp) {
     int ee_link = model.end_effectors[ee_index];
     int obj_link = model.object_joint;
@@ -278,6 +339,12 @@ template <class B> struct Assembler {
     shapePenalty(obj_link, obj_shape, c1);
     shapePenalty(ee_link, ee_shape, c2);
 
+    // friction cones: surface normal of each shape at the other side's contact point (dexlearn.h:324-362)
+    // friction cones: surface normal of each shape at the other side's contact point (dexlearn.h:324-362)
+    if (model.friction_cones) {
+      if constexpr (B::kHasCollisionOps) frictionCones(obj_link, ee_link, obj_shape, ee_shape, c1, c2, force);
+      else throw std::runtime_error("this recorder has no collision operators");
+    }
     {
       V3 d = b.vmuls(b.vsub(c2, c1), b.cs(env.contact_distance_penalty));
       b.goalV(b.vmuls(d, fx));
@@ -407,6 +474,7 @@ template <class B> struct Assembler {
           evaluateContact((int)e, cp);
         }
       }
+      collisionPenalties();  // dexlearn.h:419
       b.frameEnd(frame);
     }
 

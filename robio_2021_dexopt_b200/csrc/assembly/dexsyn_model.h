@@ -48,7 +48,15 @@ struct Shape {
   int kind = 0;  // 0 = convex polyhedron (planes), 1 = z-cylinder
   double center[3] = {0, 0, 0};
   std::vector<Plane> planes;
+  std::vector<double> points;  // polyhedron corners xyz (the support mapping of shape.h:214-222)
   double radius = 0, length = 0;
+  uint64_t handle = 0;  // in the engine's collision shape table, 0 = not registered (trx_collision_shape_create)
+};
+
+// one collision_axes instruction per frame (dexlearn.h:66-131): two links, their shapes, the registered pair
+struct CollisionPair {
+  int link_a = -1, link_b = -1;
+  uint64_t handle = 0;
 };
 
 struct Model {
@@ -60,6 +68,11 @@ struct Model {
   std::vector<int> end_effectors;       // link (= joint) indices; the last one is the floor
   std::vector<Shape> ee_shapes;         // one per end effector
   Shape object_shape;
+  // link pairs the allowed-collision matrix does not exempt (dexlearn.h:66-80); here: every finger tip and the
+  // floor against the object, and neighbouring finger tips against each other.  Filled by registerShapes().
+  std::vector<CollisionPair> collision_pairs;
+  bool wants_collision_pairs = false;
+  bool friction_cones = false;  // collision_project_2 normals + friction-cone penalties (dexlearn.h:219-233,324-362)
   // dynamic body of the object (physics5.h:78-96)
   double body_center[3] = {0, 0, 0};
   double body_mass = 0.01;
@@ -118,6 +131,11 @@ inline Shape boxShape(double sx, double sy, double sz) {
       p.d = -h[a];  // dot(n, x) + d <= 0 inside   (dexlearn.h:203-210)
       s.planes.push_back(p);
     }
+  for (int i = 0; i < 8; i++) {
+    s.points.push_back((i & 1) ? h[0] : -h[0]);
+    s.points.push_back((i & 2) ? h[1] : -h[1]);
+    s.points.push_back((i & 4) ? h[2] : -h[2]);
+  }
   return s;
 }
 
@@ -136,6 +154,8 @@ struct ModelOptions {
   int extra_fixed = 12;          // additional fixed links hung into the tree
   int policy_hidden = 64;
   bool dropout = false;
+  bool collision = false;  // collision penalties between registered link shapes (dexlearn.h:66-131)
+  bool friction = false;   // friction-cone penalties from collision_project_2 normals (dexlearn.h:324-362)
   uint64_t seed = 20211227;
 };
 
@@ -164,6 +184,8 @@ inline Model makeModel(const ModelOptions &opt) {
   Rng rng(opt.seed);
   m.policy_hidden = opt.policy_hidden;
   m.dropout = opt.dropout;
+  m.friction_cones = opt.friction;
+  m.wants_collision_pairs = opt.collision;
 
   int base = addJoint(m, rng, -1, JOINT_FIXED, "base", false, false);
   std::vector<int> tips;
@@ -303,6 +325,13 @@ struct EnvInfo {
   double time_step = 0.01;   // physics5.h:32
   double gravity[3] = {0, 0, -9.81};
   double decay = 0.01;       // physics5.h:178-186
+  // dexenv_grasp.h:25-31,43 (used when the model carries collision pairs / friction cones)
+  double collision_penalty = 1;
+  double collision_avoidance_distance = 0.01;
+  double collision_avoidance_weight = 0.02;
+  double slip_avoidance_distance = 0.01;
+  double slip_avoidance_weight = 0.1;
+  double friction_cone_penalty = 1;
 };
 
 }  // namespace dexsyn

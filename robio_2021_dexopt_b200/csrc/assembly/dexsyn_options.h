@@ -45,6 +45,8 @@ inline ProblemOptions parseProblemOptions(const char *options) {
   po.model.extra_fixed = (int)getI("extra_fixed", 12);
   po.model.policy_hidden = (int)getI("hidden", 64);
   po.model.dropout = getI("dropout", 0) != 0;
+  po.model.collision = getI("collision", 0) != 0;
+  po.model.friction = getI("friction", 0) != 0;
   po.model.seed = (uint64_t)getI("seed", 20211227);
   po.frames = (int)getI("frames", 4);
   po.outer = (int)getI("outer", 1);

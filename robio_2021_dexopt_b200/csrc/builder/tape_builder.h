@@ -37,6 +37,7 @@ class TapeBuilder {
   struct P : Handle {};
   struct M3 : Handle {};
 
+  static constexpr bool kHasCollisionOps = true;
   trxfile::Program prog;
   std::vector<uint64_t> frame_begin_inst;  // instruction count at frameBegin(t), before the passes
   // record a dense layer as one block instruction (x_dense, vm_ops.def) instead of the reference's
@@ -207,6 +208,38 @@ class TapeBuilder {
   V3 ptranslation(const P &p) { return op1<V3>("fg_pose_translation_8d", {p.addr}); }
   Q porientation(const P &p) { return op1<Q>("fg_pose_orientation_8d", {p.addr}); }
   V3 mmulv(const M3 &m, const V3 &v) { return op1<V3>("mul_fg_mat3_vec3_8d", {m.addr, v.addr}); }
+
+  // ---- collision operators (dexopt/src/ops.h:208-252,288-375).  The uint64 constant is the shape / pair handle;
+  // every instruction gets its own constant slot so that no gradient slot of a handle has two writers.
+  uint64_t cu(uint64_t v) {
+    uint64_t addr = allocS();
+    trxfile::Port c;
+    c.address = addr;
+    c.offset = prog.const_data.size();
+    c.size = 8;
+    c.lanes = 1;
+    c.elem = trxfile::ELEM_U64;
+    prog.constants.push_back(c);
+    const uint8_t *b = (const uint8_t *)&v;
+    prog.const_data.insert(prog.const_data.end(), b, b + 8);
+    return addr;
+  }
+  void collisionProject(const V3 &point, uint64_t shape, V3 &normal, S &distance) {
+    std::vector<uint64_t> outs;
+    emit("collision_project_2_8d", {point.addr, cu(shape)}, outs);
+    normal.addr = outs[0];
+    distance.addr = outs[1];
+  }
+  void collisionAxes(const P &pose_a, const P &pose_b, uint64_t pair, V3 &point_a, V3 &point_b, V3 &axis, V3 &local_a,
+                     V3 &local_b) {
+    std::vector<uint64_t> outs;
+    emit("collision_axes_8d", {pose_a.addr, pose_b.addr, cu(pair)}, outs);
+    point_a.addr = outs[0];
+    point_b.addr = outs[1];
+    axis.addr = outs[2];
+    local_a.addr = outs[3];
+    local_b.addr = outs[4];
+  }
 
   // ---- dense layer, expanded exactly like the reference records it
   // (dexopt/src/tensor.h:134-172 and dexopt/src/neural.h:176-181)

@@ -131,6 +131,10 @@ inline Plan makePlan(const dexsyn::Model &m, const dexsyn::EnvInfo &env, int fra
     p.error = "dropout masks are per-lane parameters of the flat tape only";
     return p;
   }
+  if (m.wants_collision_pairs || m.friction_cones) {
+    p.error = "collision and friction-cone penalties (collision_axes, collision_project_2) run on the flat tape only";
+    return p;
+  }
   const int n_all = (int)m.joints.size();
   // ---- which links does the objective look at?  (everything else is dead code on the reference tape too)
   std::vector<char> need(n_all, 0);

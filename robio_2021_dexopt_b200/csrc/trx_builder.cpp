@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/trx_b200.h"
 #include "assembly/dexsyn_assemble.h"
@@ -13,6 +14,44 @@
 
 namespace {
 thread_local std::string g_builder_error;
+}
+
+// Registers the model's link shapes with the engine's collision shape table (what CollisionRobot does from the
+// URDF meshes in the reference, src/collision/robot.cpp:60-140) and lists the link pairs to test: every end effector
+// (finger tips, floor) against the object, and neighbouring finger tips against each other.
+static void registerShapes(dexsyn::Model &model) {
+  if (!model.wants_collision_pairs && !model.friction_cones) return;
+  auto reg = [](dexsyn::Shape &s) {
+    trx_shape_desc d;
+    std::memset(&d, 0, sizeof(d));
+    std::vector<double> planes;
+    if (s.kind == 1) {
+      d.kind = TRX_SHAPE_CYLINDER;
+      d.radius = s.radius;
+      d.length = s.length;
+    } else {
+      d.kind = TRX_SHAPE_POLYHEDRON;
+      for (auto &pl : s.planes) planes.insert(planes.end(), {pl.n[0], pl.n[1], pl.n[2], pl.d});
+      d.n_points = (uint32_t)(s.points.size() / 3);
+      d.n_planes = (uint32_t)s.planes.size();
+      d.points = s.points.data();
+      d.planes = planes.data();
+    }
+    if (trx_collision_shape_create(&d, &s.handle) != TRX_OK) throw std::runtime_error(trx_last_error());
+  };
+  reg(model.object_shape);
+  for (auto &s : model.ee_shapes) reg(s);
+  if (!model.wants_collision_pairs) return;
+  auto pair = [&](int ea, const dexsyn::Shape &sa, int link_b, const dexsyn::Shape &sb) {
+    dexsyn::CollisionPair cp;
+    cp.link_a = model.end_effectors[ea];
+    cp.link_b = link_b;
+    if (trx_collision_pair_create(sa.handle, sb.handle, &cp.handle) != TRX_OK) throw std::runtime_error(trx_last_error());
+    model.collision_pairs.push_back(cp);
+  };
+  const int n_ee = (int)model.end_effectors.size();
+  for (int e = 0; e < n_ee; e++) pair(e, model.ee_shapes[e], model.object_joint, model.object_shape);
+  for (int e = 0; e + 2 < n_ee; e++) pair(e, model.ee_shapes[e], model.end_effectors[e + 1], model.ee_shapes[e + 1]);
 }
 
 extern "C" {
@@ -53,11 +92,14 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     mo.extra_fixed = (int)getI("extra_fixed", 12);
     mo.policy_hidden = (int)getI("hidden", 64);
     mo.dropout = getI("dropout", 0) != 0;
+    mo.collision = getI("collision", 0) != 0;
+    mo.friction = getI("friction", 0) != 0;
     mo.seed = (uint64_t)getI("seed", 20211227);
     int frames = (int)getI("frames", 4);
     int outer = (int)getI("outer", 1);
     double wstd = getD("wstd", 0.1);
     dexsyn::Model model = dexsyn::makeModel(mo);
+    registerShapes(model);
     size_t np = dexsyn::Assembler<trxb::TapeBuilder>::parameterCount(model);
     dexsyn::Rng rng(mo.seed + 1);
     std::vector<double> x0(np);

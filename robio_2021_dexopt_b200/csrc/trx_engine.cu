@@ -31,6 +31,7 @@
 #include "trx_direct.h"
 #include "vm_exec.cuh"
 #include "trx_comm.h"
+#include "collision/trx_shape_table.h"
 #include "trx_rollout.h"
 
 namespace {
@@ -930,6 +931,7 @@ trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer) {
 static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int scalar_in, int scalar_out,
                                 trx_program **out);
 
+static trx_status checkShapeHandles(const trxfile::Program &src);
 static trx_status createFromFile(const trxfile::Program &src, int device, int scalar_in, int scalar_out,
                                  trx_program **out, bool fold_accumulate = false) {
   if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
@@ -957,6 +959,10 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     std::string msg = e.what();
     bool unsupported = msg.find("unsupported operator") != std::string::npos;
     return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, msg);
+  }
+  if (p->low.uses_shapes) {
+    trx_status cs = checkShapeHandles(src);
+    if (cs != TRX_OK) return cs;
   }
   return finishProgram(p, device, scalar_in, scalar_out, out);
 }
@@ -1148,6 +1154,68 @@ trx_status trx_execute(const trx_program *p, trx_memory *m, void *stream_) { ret
 // that nothing has overwritten them (objectives, after their first evaluation)
 static std::atomic<uint64_t> g_rng_seed{0x9E3779B97F4A7C15ull}, g_rng_epoch{0};
 
+// ---- collision shape table (include/trx_b200.h, csrc/collision/trx_collide.h): one host copy, one mirror per device
+struct ShapeRegistry {
+  std::mutex mu;
+  trxcol::ShapeTable table;
+  uint64_t version = 1;
+  struct Mirror {
+    double *d = nullptr;
+    uint64_t version = 0, capacity = 0;
+  } mirror[64];
+};
+static ShapeRegistry &shapeRegistry() {
+  static ShapeRegistry r;
+  return r;
+}
+// makes the device's copy current and points the kernels' symbol at it (ordered on `stream`)
+static trx_status syncShapeTable(int device, cudaStream_t stream) {
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  if (device < 0 || device >= 64) return fail(TRX_ERR_INVALID, "device index out of range");
+  auto &M = R.mirror[device];
+  if (M.version == R.version) return TRX_OK;
+  if (M.capacity < R.table.heap.size()) {
+    // (an old table may still be read by work in flight: it is left to the process' end rather than freed)
+    M.capacity = std::max<uint64_t>(2 * R.table.heap.size(), 1024);
+    TRX_CUDA(cudaMalloc(&M.d, M.capacity * sizeof(double)));
+  }
+  TRX_CUDA(cudaMemcpyAsync(M.d, R.table.heap.data(), R.table.heap.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+  TRX_CUDA(cudaStreamSynchronize(stream));  // the host vector may grow once the lock is released
+  const double *ptr = M.d;
+  TRX_CUDA(cudaMemcpyToSymbolAsync(trxvm::g_shape_heap_dev, &ptr, sizeof(ptr), 0, cudaMemcpyHostToDevice, stream));
+  M.version = R.version;
+  return TRX_OK;
+}
+// every uint64 constant that a collision instruction reads must be a registered handle of the right kind
+static trx_status checkShapeHandles(const trxfile::Program &src) {
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  std::unordered_map<uint64_t, uint64_t> const_at;  // address -> bits
+  for (auto &c : src.constants)
+    if (c.size == 8 && c.offset + 8 <= src.const_data.size()) {
+      uint64_t bits;
+      memcpy(&bits, src.const_data.data() + c.offset, 8);
+      const_at[c.address] = bits;
+    }
+  uint64_t pc = 0;
+  while (pc < src.code.size()) {  // (lowerProgram has validated the code words)
+    const auto &op = src.ops[src.code[pc]];
+    const bool axes = op.name.rfind("collision_axes_", 0) == 0, proj = op.name.rfind("collision_project_2_", 0) == 0;
+    if (axes || proj) {
+      auto it = const_at.find(src.code[pc + 1 + (axes ? 2 : 1)]);
+      if (it == const_at.end())
+        return fail(TRX_ERR_INVALID, op.name + ": the shape argument is not a constant of the program");
+      const auto &known = axes ? R.table.pairs : R.table.shapes;
+      if (std::find(known.begin(), known.end(), it->second) == known.end())
+        return fail(TRX_ERR_INVALID, op.name + ": constant " + std::to_string(it->second) +
+                                         " is not a handle from trx_collision_" + (axes ? "pair" : "shape") + "_create");
+    }
+    pc += 1 + op.args.size();
+  }
+  return TRX_OK;
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: remember which devices have it
 static bool firstUseOnDevice(int device, int which) {
   static std::mutex mu;
@@ -1182,6 +1250,10 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
     st.tile_stride = m->tile_stride;
     st.lane_base = m->rng_lane_base;
     TRX_CUDA(cudaMemcpyToSymbolAsync(trxvm::g_rng_dev, &st, sizeof(st), 0, cudaMemcpyHostToDevice, stream));
+  }
+  if (p->low.uses_shapes) {
+    trx_status cs = syncShapeTable(m->device, stream);
+    if (cs != TRX_OK) return cs;
   }
   uint32_t nc = upload_constants ? (uint32_t)p->low.const_idx.size() : 0;
   if (nc) {
@@ -1553,6 +1625,115 @@ trx_status trx_objective_parameterize(trx_objective *o, const void *packed, uint
 void trx_set_random_seed(uint64_t seed) {
   g_rng_seed.store(seed);
   g_rng_epoch.store(0);
+}
+
+// ---- collision shapes
+trx_status trx_collision_shape_create(const trx_shape_desc *d, uint64_t *handle) {
+  if (!d || !handle) return fail(TRX_ERR_INVALID, "bad argument");
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  bool unsupported = false;
+  const std::string err = R.table.addShape(*d, *handle, unsupported);
+  if (!err.empty()) return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, err);
+  R.version++;
+  trxvm::shapeHeapHost() = R.table.heap.data();
+  return TRX_OK;
+}
+
+trx_status trx_collision_pair_create(uint64_t a, uint64_t b, uint64_t *handle) {
+  if (!handle) return fail(TRX_ERR_INVALID, "bad argument");
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  const std::string err = R.table.addPair(a, b, *handle);
+  if (!err.empty()) return fail(TRX_ERR_INVALID, err);
+  R.version++;
+  trxvm::shapeHeapHost() = R.table.heap.data();
+  return TRX_OK;
+}
+
+trx_status trx_collision_shape_center(uint64_t shape, double *center3) {
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  if (!center3 || std::find(R.table.shapes.begin(), R.table.shapes.end(), shape) == R.table.shapes.end())
+    return fail(TRX_ERR_INVALID, "not a shape handle");
+  for (int k = 0; k < 3; k++) center3[k] = R.table.heap[shape + trxcol::REC_CENTER + k];
+  return TRX_OK;
+}
+
+void trx_collision_clear(void) {
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  R.table.clear();
+  R.version++;
+  trxvm::shapeHeapHost() = R.table.heap.data();
+}
+
+trx_status trx_collision_table(double *out, uint64_t capacity, uint64_t *count) {
+  if (!count) return fail(TRX_ERR_INVALID, "bad argument");
+  ShapeRegistry &R = shapeRegistry();
+  std::lock_guard<std::mutex> lock(R.mu);
+  *count = R.table.heap.size();
+  if (out) std::memcpy(out, R.table.heap.data(), std::min<uint64_t>(capacity, *count) * sizeof(double));
+  return TRX_OK;
+}
+
+__global__ void trx_collision_pairs_kernel(uint64_t pair, const double *poses, uint64_t n, double *out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *q = poses + 14 * i;
+  trxvm::PoseV a, b;
+  a.t = trxvm::V3{q[0], q[1], q[2]}, a.r = trxvm::Q4{q[3], q[4], q[5], q[6]};
+  b.t = trxvm::V3{q[7], q[8], q[9]}, b.r = trxvm::Q4{q[10], q[11], q[12], q[13]};
+  trxcol::Result r;
+  trxcol::collideShapes(trxvm::g_shape_heap_dev, pair, a, b, r);
+  double *o = out + 10 * i;
+  o[0] = r.a.x, o[1] = r.a.y, o[2] = r.a.z, o[3] = r.b.x, o[4] = r.b.y, o[5] = r.b.z;
+  o[6] = r.n.x, o[7] = r.n.y, o[8] = r.n.z, o[9] = r.d;
+}
+__global__ void trx_collision_project_kernel(uint64_t shape, const double *points, uint64_t n, double *out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  trxvm::V3 nrm = trxvm::V3{0.0, 0.0, 0.0};
+  double d = 0.0;
+  trxcol::projectPoint(trxvm::g_shape_heap_dev, shape, trxvm::V3{points[3 * i], points[3 * i + 1], points[3 * i + 2]}, nrm, d);
+  out[4 * i] = nrm.x, out[4 * i + 1] = nrm.y, out[4 * i + 2] = nrm.z, out[4 * i + 3] = d;
+}
+
+static trx_status collisionBatch(bool pairs, uint64_t handle, const double *in, uint64_t n, double *out, int device) {
+  if ((!in || !out) && n) return fail(TRX_ERR_INVALID, "bad argument");
+  {
+    ShapeRegistry &R = shapeRegistry();
+    std::lock_guard<std::mutex> lock(R.mu);
+    const auto &known = pairs ? R.table.pairs : R.table.shapes;
+    if (std::find(known.begin(), known.end(), handle) == known.end()) return fail(TRX_ERR_INVALID, "unknown handle");
+  }
+  if (n == 0) return TRX_OK;
+  TRX_CUDA(cudaSetDevice(device));
+  trx_status s = syncShapeTable(device, 0);
+  if (s != TRX_OK) return s;
+  const size_t in_w = pairs ? 14 : 3, out_w = pairs ? 10 : 4;
+  double *d_in = nullptr, *d_out = nullptr;
+  TRX_CUDA(cudaMalloc(&d_in, n * in_w * sizeof(double)));
+  if (cudaMalloc(&d_out, n * out_w * sizeof(double)) != cudaSuccess) {
+    cudaFree(d_in);
+    return fail(TRX_ERR_CUDA, "out of device memory");
+  }
+  cudaMemcpy(d_in, in, n * in_w * sizeof(double), cudaMemcpyHostToDevice);
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (pairs) trx_collision_pairs_kernel<<<blocks, 128>>>(handle, d_in, n, d_out);
+  else trx_collision_project_kernel<<<blocks, 128>>>(handle, d_in, n, d_out);
+  g_launches++;
+  cudaError_t e = cudaMemcpy(out, d_out, n * out_w * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(TRX_ERR_CUDA, cudaGetErrorString(e));
+  return TRX_OK;
+}
+trx_status trx_collision_query_pairs(uint64_t pair, const double *poses, uint64_t n, double *out, int device) {
+  return collisionBatch(true, pair, poses, n, out, device);
+}
+trx_status trx_collision_project_points(uint64_t shape, const double *points, uint64_t n, double *out, int device) {
+  return collisionBatch(false, shape, points, n, out, device);
 }
 
 // ---- communicator

@@ -147,6 +147,7 @@ struct LoweredProgram {
   uint64_t n_ring_reads = 0, n_image_reads = 0, n_ring_only_writes = 0, n_dual_writes = 0, n_image_writes = 0;
   bool has_forward = false, has_reverse = false;
   bool draws_random = false;  // add_random_* / dropout2 on the tape: the executor sets the generator state per execute
+  bool uses_shapes = false;   // collision_axes / collision_project_2 on the tape: the executor mirrors the shape table
   PortLayout inputs, parameters, outputs;
   std::vector<uint32_t> const_idx;
   std::vector<uint64_t> const_bits;
@@ -195,6 +196,7 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
     const std::string base_name = sig.base;  // (a string, not the table's pointer)
     if (sig.mode == 'C' && (base_name == "add_random_normal" || base_name == "add_random_uniform" || base_name == "dropout2"))
       out.draws_random = true;
+    if (sig.mode == 'C' && (base_name == "collision_axes" || base_name == "collision_project_2")) out.uses_shapes = true;
     if (sig.mode == 'F') out.has_forward = true;
     if (sig.mode == 'R') out.has_reverse = true;
   }

@@ -8,9 +8,11 @@
 // with cs = 8 for lane-typed (*_8d) operators and cs = 1 for scalar (*_d) ones.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "trx_ops.h"
 #include "vm_math.cuh"
+#include "collision/trx_collide.h"
 
 namespace trxvm {
 
@@ -230,6 +232,34 @@ TRX_HD double rng_normal(const C &c, int kout) {
   double u0, u1;
   rng_uniform2(c, kout, u0, u1);
   return sqrt(-2.0 * log(1.0 - u0)) * cos(6.283185307179586476925286766559 * u1);
+}
+
+// ---- collision shapes (collision/trx_collide.h): the table the host registered, mirrored to the device before a
+// program with collision operators runs (trx_engine.cu executeImpl).  uint64-typed arguments are one slot per
+// instruction holding the integer's bits.
+#ifdef __CUDACC__
+__device__ const double *g_shape_heap_dev;
+#endif
+inline const double *&shapeHeapHost() {
+  static const double *heap = nullptr;
+  return heap;
+}
+TRX_HD const double *shapeHeap() {
+#ifdef __CUDA_ARCH__
+  return g_shape_heap_dev;
+#else
+  return shapeHeapHost();
+#endif
+}
+template <class C>
+TRX_HD uint64_t ldu(const C &c, int k) {
+#ifdef __CUDA_ARCH__
+  return (uint64_t)__double_as_longlong(c.m[argword(c, k)]);
+#else
+  uint64_t bits;
+  memcpy(&bits, &c.m[argword(c, k)], sizeof(bits));
+  return bits;
+#endif
 }
 
 // number of arguments in a signature string (tokens separated by single blanks)

@@ -22,6 +22,8 @@ def _build_emulator():
         os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "vm_ops.def"),
         os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "vm_exec.cuh"),
         os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "vm_math.cuh"),
+        os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "collision", "trx_collide.h"),
+        os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "collision", "trx_shape_table.h"),
         os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "trx_lower.h"),
         os.path.join(ROOT, "robio_2021_dexopt_b200", "csrc", "trx_ops.h"),
         os.path.join(ROOT, "include", "trx_file.h"),

@@ -17,6 +17,7 @@
 #include "../../include/trx_b200.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_lower.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_fuse.h"
+#include "../../robio_2021_dexopt_b200/csrc/collision/trx_shape_table.h"
 #include "../../robio_2021_dexopt_b200/csrc/trx_direct.h"
 #include "../../robio_2021_dexopt_b200/csrc/vm_exec.cuh"
 
@@ -265,6 +266,65 @@ void emu_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) 
   uint32_t o[4];
   trxvm::philox4x32_10(c, k, o);
   for (int i = 0; i < 4; i++) out[i] = o[i];
+}
+
+// collision shapes: the emulator's own table (same record builder as the library), and the two queries on the host
+static trxcol::ShapeTable g_emu_shapes;
+int emu_collision_shape_create(const trx_shape_desc *d, uint64_t *handle) {
+  bool unsupported = false;
+  const std::string err = g_emu_shapes.addShape(*d, *handle, unsupported);
+  trxvm::shapeHeapHost() = g_emu_shapes.heap.data();
+  return err.empty() ? 0 : fail(unsupported ? -2 : -1, err);
+}
+int emu_collision_pair_create(uint64_t a, uint64_t b, uint64_t *handle) {
+  const std::string err = g_emu_shapes.addPair(a, b, *handle);
+  trxvm::shapeHeapHost() = g_emu_shapes.heap.data();
+  return err.empty() ? 0 : fail(-1, err);
+}
+void emu_collision_clear() {
+  g_emu_shapes.clear();
+  trxvm::shapeHeapHost() = g_emu_shapes.heap.data();
+}
+// a copy of the library's table (trx_collision_table), so that tapes built by the product recorder find their handles
+void emu_collision_set_table(const double *heap, uint64_t n) {
+  g_emu_shapes.clear();
+  g_emu_shapes.heap.assign(heap, heap + n);
+  for (uint64_t at = 1; at < n;) {  // walk the records to list the handles
+    if ((int)heap[at] == trxcol::SHAPE_PAIR) {
+      g_emu_shapes.pairs.push_back(at);
+      at += trxcol::PAIR_SIZE;
+    } else {
+      g_emu_shapes.shapes.push_back(at);
+      at += trxcol::REC_DATA + 3 * (uint64_t)heap[at + trxcol::REC_NPOINTS] + 4 * (uint64_t)heap[at + trxcol::REC_NPLANES];
+    }
+  }
+  trxvm::shapeHeapHost() = g_emu_shapes.heap.data();
+}
+// out = n x 12: a, b, normal, distance, gjk iterations, epa iterations
+int emu_collision_query_pairs(uint64_t pair, const double *poses, uint64_t n, double *out) {
+  if (!g_emu_shapes.isPair(pair)) return fail(-1, "unknown handle");
+  for (uint64_t i = 0; i < n; i++) {
+    const double *q = poses + 14 * i;
+    trxvm::PoseV a, b;
+    a.t = trxvm::V3{q[0], q[1], q[2]}, a.r = trxvm::Q4{q[3], q[4], q[5], q[6]};
+    b.t = trxvm::V3{q[7], q[8], q[9]}, b.r = trxvm::Q4{q[10], q[11], q[12], q[13]};
+    trxcol::Result r;
+    trxcol::collideShapes(g_emu_shapes.heap.data(), pair, a, b, r);
+    double *o = out + 12 * i;
+    o[0] = r.a.x, o[1] = r.a.y, o[2] = r.a.z, o[3] = r.b.x, o[4] = r.b.y, o[5] = r.b.z;
+    o[6] = r.n.x, o[7] = r.n.y, o[8] = r.n.z, o[9] = r.d, o[10] = r.gjk_iterations, o[11] = r.epa_iterations;
+  }
+  return 0;
+}
+int emu_collision_project_points(uint64_t shape, const double *points, uint64_t n, double *out) {
+  if (!g_emu_shapes.isShape(shape)) return fail(-1, "unknown handle");
+  for (uint64_t i = 0; i < n; i++) {
+    trxvm::V3 nrm = trxvm::V3{0.0, 0.0, 0.0};
+    double d = 0.0;
+    trxcol::projectPoint(g_emu_shapes.heap.data(), shape, trxvm::V3{points[3 * i], points[3 * i + 1], points[3 * i + 2]}, nrm, d);
+    out[4 * i] = nrm.x, out[4 * i + 1] = nrm.y, out[4 * i + 2] = nrm.z, out[4 * i + 3] = d;
+  }
+  return 0;
 }
 
 int emu_execute(const emu_program *p, emu_memory *m) {
