@@ -31,6 +31,20 @@
 
 #include "../include/trx_b200.h"
 
+// Tapes with collision_axes / collision_project_2 (dexopt/src/ops.h:208-375) carry the addresses of host objects
+// (CollisionShape<double>*, ShapeCollisionPair<double>*) as uint64 constants.  Where the reference's collision
+// headers are available (they need Eigen; the queries themselves no longer need Bullet), define
+// TRX_WITH_TRACTOR_COLLISION before including this file: _compile then registers every such object with the
+// library's shape table (trx_collision_shape_create / _pair_create) and hands the device the handles instead.
+// Without the macro such a tape is refused by trx_program_create ("not a handle").  This block cannot be compiled
+// in an image without Eigen and is therefore exercised only through the C ABI (tests/test_collision.py).
+#ifdef TRX_WITH_TRACTOR_COLLISION
+#include <map>
+#include <cstring>
+#include <tractor/collision/query.h>
+#include <tractor/collision/shape.h>
+#endif
+
 namespace tractor {
 
 class CudaEngine : public Engine {
@@ -86,6 +100,70 @@ class CudaEngine : public Engine {
     }
     static trx_memory *mem(const std::shared_ptr<Memory> &m) { return static_cast<MemoryImpl *>(m.get())->handle; }
 
+#ifdef TRX_WITH_TRACTOR_COLLISION
+    // one table entry per host object, process-wide (the same shape is shared by many instructions and programs)
+    static uint64_t shapeHandle(const CollisionShape<double> *shape) {
+      static std::map<const void *, uint64_t> known;
+      auto it = known.find(shape);
+      if (it != known.end()) return it->second;
+      trx_shape_desc d{};
+      std::vector<double> points, planes;
+      if (auto *cyl = dynamic_cast<const CollisionCylinderShape<double> *>(shape)) {
+        d.kind = TRX_SHAPE_CYLINDER;
+        d.radius = cyl->radius();
+        d.length = cyl->length();
+      } else if (auto *mesh = dynamic_cast<const ConvexPolyhedralCollisionShape<double> *>(shape)) {
+        d.kind = TRX_SHAPE_POLYHEDRON;
+        for (auto &p : mesh->points()) points.insert(points.end(), {p.x(), p.y(), p.z()});
+        for (auto &pl : mesh->planes())
+          planes.insert(planes.end(), {pl.normal().x(), pl.normal().y(), pl.normal().z(), pl.offset()});
+        d.n_points = (uint32_t)mesh->points().size();
+        d.n_planes = (uint32_t)mesh->planes().size();
+        d.points = points.data();
+        d.planes = planes.data();
+      } else if (dynamic_cast<const CollisionSphereShape<double> *>(shape)) {
+        // the radius has no accessor: support(+x) = centre + radius * x (shape.h:60-63)
+        d.kind = TRX_SHAPE_SPHERE;
+        auto c = shape->center();
+        auto s = shape->support(Vector3<double>(1, 0, 0));
+        d.center[0] = c.x(), d.center[1] = c.y(), d.center[2] = c.z();
+        d.radius = s.x() - c.x();
+      } else {
+        throw std::runtime_error("CudaEngine: collision shape not yet supported");  // as dexlearn.h:212-216
+      }
+      uint64_t h = 0;
+      check(trx_collision_shape_create(&d, &h));
+      return known[shape] = h;
+    }
+    static uint64_t pairHandle(const ShapeCollisionPair<double> *pair) {
+      static std::map<const void *, uint64_t> known;
+      auto it = known.find(pair);
+      if (it != known.end()) return it->second;
+      uint64_t h = 0;
+      check(trx_collision_pair_create(shapeHandle(pair->shapeA().get()), shapeHandle(pair->shapeB().get()), &h));
+      return known[pair] = h;
+    }
+    // rewrites, in a copy of the constant blob, the uint64 constants that collision instructions read
+    static std::vector<uint8_t> translateShapeConstants(const Program &program) {
+      std::vector<uint8_t> blob(program.constData().begin(), program.constData().end());
+      for (auto &inst : program.instructions()) {
+        const std::string &name = inst.op()->name();
+        const bool axes = name.rfind("collision_axes_", 0) == 0, proj = name.rfind("collision_project_2_", 0) == 0;
+        if (!axes && !proj) continue;
+        const uint64_t slot = (uint64_t)inst.args()[axes ? 2 : 1];
+        for (auto &c : program.constants()) {
+          if (c.address() != slot) continue;
+          uint64_t bits = 0;
+          std::memcpy(&bits, blob.data() + c.offset(), 8);
+          const uint64_t h = axes ? pairHandle((const ShapeCollisionPair<double> *)bits)
+                                  : shapeHandle((const CollisionShape<double> *)bits);
+          std::memcpy(blob.data() + c.offset(), &h, 8);
+        }
+      }
+      return blob;
+    }
+#endif
+
    protected:
     void _compile(const Program &program) override {
       std::vector<const Operator *> op_list;
@@ -137,6 +215,10 @@ class CudaEngine : public Engine {
       d.constants = con.data();
       d.n_const_data = program.constData().size();
       d.const_data = program.constData().data();
+#ifdef TRX_WITH_TRACTOR_COLLISION
+      const std::vector<uint8_t> translated = translateShapeConstants(program);
+      d.const_data = translated.data();
+#endif
       if (_program) trx_program_destroy(_program);
       _program = nullptr;
       check(trx_program_create(&d, _device, &_program));
