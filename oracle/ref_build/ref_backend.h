@@ -12,8 +12,10 @@
 namespace refc {
 
 template <class Lane> struct RefBackend {
-  // collision_axes / collision_project_2 call Bullet in the reference (src/collision/query.cpp): not buildable here
-  static constexpr bool kHasCollisionOps = false;
+  // collision_axes / collision_project_2 are the reference's operators (dexopt/src/ops.h:208-375) over the stand-in
+  // shape classes of shim/tractor_collision/collision_decl.h; the uint64 the assembly passes is the address of such
+  // an object, as in the reference (dexlearn.h:85-93,329)
+  static constexpr bool kHasCollisionOps = true;
   typedef Lane LaneValue;  // tractor::Batch8d
   typedef tractor::Var<Lane> S;
   typedef tractor::Var<double> W;
@@ -112,6 +114,15 @@ template <class Lane> struct RefBackend {
   V3 ptranslation(const P &p) { return tractor::fg_pose_translation(p); }
   Q porientation(const P &p) { return tractor::fg_pose_orientation(p); }
   V3 mmulv(const M3 &m, const V3 &v) { return tractor::mul(m, v); }
+
+  // ---- collision operators (dexopt/src/ops.h:208-252,288-375), called as dexlearn.h:93-95,329-330 call them
+  void collisionProject(const V3 &point, uint64_t shape, V3 &normal, S &distance) {
+    tractor::collision_project_2(nc(point), shape, normal, distance);
+  }
+  void collisionAxes(const P &pose_a, const P &pose_b, uint64_t pair, V3 &point_a, V3 &point_b, V3 &axis, V3 &local_a,
+                     V3 &local_b) {
+    tractor::collision_axes(nc(pose_a), nc(pose_b), pair, point_a, point_b, axis, local_a, local_b);
+  }
 
   // ---- dense layer: tensor_mul_vec_mat (dexopt/src/tensor.h:134-172) + bias
   // broadcast/add (dexopt/src/neural.h:176-181), weights[row * n_out + col]

@@ -19,6 +19,8 @@
 //
 // TEST INFRASTRUCTURE ONLY.
 #include <atomic>
+#include <cstring>
+#include <deque>
 #include <fstream>
 #include <mutex>
 #include <thread>
@@ -26,8 +28,78 @@
 #include "ref_backend.h"
 #include "../../robio_2021_dexopt_b200/csrc/assembly/dexsyn_assemble.h"
 
+#include "../../robio_2021_dexopt_b200/csrc/collision/trx_shape_table.h"
+
 using namespace refc;
 typedef tractor::Batch8d Lane;
+
+// ---- collision problems: the model's shapes as stand-in reference objects whose queries go through the hook
+// (shim/tractor_collision/collision_decl.h).  The hook is answered by the geometric query under test
+// (csrc/collision/trx_collide.h, compiled here for the host) -- parity of that arithmetic against Bullet stays
+// unpinned; everything around it on the tape is the reference's own code.
+static trxcol::ShapeTable g_shapes;
+static std::deque<tractor::CollisionShape<double>> g_shape_objects;
+static std::deque<tractor::ShapeCollisionPair<double>> g_pair_objects;
+static void hookProject(uint64_t shape, const double *p, double *n, double *d) {
+  trxvm::V3 nrm{0, 0, 0};
+  double dist = 0;
+  trxcol::projectPoint(g_shapes.heap.data(), shape, trxvm::V3{p[0], p[1], p[2]}, nrm, dist);
+  n[0] = nrm.x, n[1] = nrm.y, n[2] = nrm.z, *d = dist;
+}
+static void hookPair(uint64_t pair, const double *pa, const double *pb, double *a, double *b, double *n) {
+  trxvm::PoseV A, B;
+  A.t = {pa[0], pa[1], pa[2]}, A.r = {pa[3], pa[4], pa[5], pa[6]};
+  B.t = {pb[0], pb[1], pb[2]}, B.r = {pb[3], pb[4], pb[5], pb[6]};
+  trxcol::Result r;
+  trxcol::collideShapes(g_shapes.heap.data(), pair, A, B, r);
+  a[0] = r.a.x, a[1] = r.a.y, a[2] = r.a.z, b[0] = r.b.x, b[1] = r.b.y, b[2] = r.b.z, n[0] = r.n.x, n[1] = r.n.y, n[2] = r.n.z;
+}
+// the same shapes and pairs, in the same order, as csrc/trx_builder.cpp registerShapes()
+static void registerShapes(dexsyn::Model &model) {
+  if (!model.wants_collision_pairs && !model.friction_cones) return;
+  tractor::collisionQueryHook().project = hookProject;
+  tractor::collisionQueryHook().pair = hookPair;
+  auto reg = [](dexsyn::Shape &s) {
+    trx_shape_desc d;
+    std::memset(&d, 0, sizeof(d));
+    std::vector<double> planes;
+    if (s.kind == 1) {
+      d.kind = TRX_SHAPE_CYLINDER, d.radius = s.radius, d.length = s.length;
+    } else {
+      d.kind = TRX_SHAPE_POLYHEDRON;
+      for (auto &pl : s.planes) planes.insert(planes.end(), {pl.n[0], pl.n[1], pl.n[2], pl.d});
+      d.n_points = (uint32_t)(s.points.size() / 3), d.n_planes = (uint32_t)s.planes.size();
+      d.points = s.points.data(), d.planes = planes.data();
+    }
+    uint64_t h = 0;
+    bool unsupported = false;
+    std::string err = g_shapes.addShape(d, h, unsupported);
+    if (!err.empty()) throw std::runtime_error(err);
+    g_shape_objects.emplace_back();
+    g_shape_objects.back().handle = h;
+    s.handle = (uint64_t)&g_shape_objects.back();  // the tape carries the object's address (dexlearn.h:329)
+    return h;
+  };
+  const uint64_t h_obj = reg(model.object_shape);
+  std::vector<uint64_t> h_ee;
+  for (auto &s : model.ee_shapes) h_ee.push_back(reg(s));
+  if (!model.wants_collision_pairs) return;
+  auto pair = [&](int ea, uint64_t ha, int link_b, uint64_t hb) {
+    dexsyn::CollisionPair cp;
+    cp.link_a = model.end_effectors[ea];
+    cp.link_b = link_b;
+    uint64_t h = 0;
+    std::string err = g_shapes.addPair(ha, hb, h);
+    if (!err.empty()) throw std::runtime_error(err);
+    g_pair_objects.emplace_back();
+    g_pair_objects.back().handle = h;
+    cp.handle = (uint64_t)&g_pair_objects.back();
+    model.collision_pairs.push_back(cp);
+  };
+  const int n_ee = (int)model.end_effectors.size();
+  for (int e = 0; e < n_ee; e++) pair(e, h_ee[e], model.object_joint, h_obj);
+  for (int e = 0; e + 2 < n_ee; e++) pair(e, h_ee[e], model.end_effectors[e + 1], h_ee[e + 1]);
+}
 
 static std::map<std::string, std::string> parseArgs(int argc, char **argv, int first) {
   std::map<std::string, std::string> kv;
@@ -240,11 +312,14 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
   mo.extra_fixed = (int)getI(kv, "extra_fixed", 12);
   mo.policy_hidden = (int)getI(kv, "hidden", 64);
   mo.dropout = getI(kv, "dropout", 0) != 0;
+  mo.collision = getI(kv, "collision", 0) != 0;
+  mo.friction = getI(kv, "friction", 0) != 0;
   mo.seed = (uint64_t)getI(kv, "seed", 20211227);
   int frames = (int)getI(kv, "frames", 4);
   int outer = (int)getI(kv, "outer", 1);
   double wstd = getD(kv, "wstd", 0.1);
   g_model = dexsyn::makeModel(mo);
+  registerShapes(g_model);
   size_t np = dexsyn::Assembler<RefBackend<Lane>>::parameterCount(g_model);
   dexsyn::Rng rng(mo.seed + 1);
   x0.resize(np);

@@ -24,4 +24,8 @@ $R record $G/rollout_chain30.trxb problem=dexsyn kind=chain joints=30 contacts=1
 $R record $G/rollout_handarm_long.trxb problem=dexsyn kind=handarm hidden=8 frames=24 tiles=1 programs=0 keep_dr=0
 # LeastSquaresSolver iterates of the dexsyn_small problem (values only): reference engine work, restated Eigen CG
 $R record $G/sq_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 sq_steps=3 programs=0 keep_dr=0
+# the dexsyn_small problem with collision and friction-cone penalties (dexlearn.h:66-131,219-233,324-362), values only:
+# reference operators, gradients and engine; the Bullet call inside them answered through the hook of
+# oracle/ref_build/shim/tractor_collision/collision_decl.h by csrc/collision/trx_collide.h (parity of that query unpinned)
+$R record $G/dexsyn_collision.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 collision=1 friction=1 gd_steps=10 programs=0 gd_keep=last
 ls -la $G

@@ -365,6 +365,23 @@ def test_unregistered_handles_are_rejected_at_compile_time():
     assert e.value.status in (-1, -3)
 
 
+def test_collision_problem_matches_the_reference_engine(emu_engine, golden):
+    """tests/golden/dexsyn_collision.trxb: the SAME problem recorded through the reference's Var<> API with the
+    reference's collision operators (ops.h:208-375 over stand-in shape classes whose one Bullet call is answered by
+    the query under test), differentiated by the reference's buildGradients and run by the reference's SimpleEngine.
+    The product's recorder + gradients + VM must give its residuals, loss, J^T r and J dx: everything around the
+    geometric query -- operator bodies, derivative rules as written, the penalty assembly -- is pinned to the
+    reference's own code; the query's arithmetic against Bullet's is what stays unpinned."""
+    import parity
+    ref = golden("dexsyn_collision.trxb")
+    mine = build_collision_problem()
+    use_library_table(emu_engine)
+    for k, v in ref.arrays.items():
+        mine.arrays.setdefault(k, v)
+    r, g = parity.check_problem(emu_engine, mine, check_tangent=True)
+    assert r.size == 24727 and g.size == 583
+
+
 # ---------------------------------------------------------------- GPU: the product library
 class DeviceQueries:
     def project(self, shape, pts):
@@ -485,3 +502,23 @@ def test_rollout_objective_refuses_collision_problems(cuda_engine):
     with pytest.raises(pkg.TrxError) as e:
         pkg.RolloutObjective(cuda_engine, 16, frames=2, hidden=4, collision=1)
     assert e.value.status == -2
+
+
+@pytest.mark.gpu
+def test_collision_problem_matches_the_reference_engine_on_the_device(cuda_engine, golden):
+    """the device against the reference engine's numbers for the collision problem (see the CPU test of the same
+    name): residuals, loss, gradient, tangent through the executables, and ten gradient-descent iterates through
+    the device-resident solver"""
+    import parity
+    import robio_2021_dexopt_b200 as pkg
+    from robio_2021_dexopt_b200 import trxfile
+    ref = golden("dexsyn_collision.trxb")
+    mine = build_collision_problem()
+    for k, v in ref.arrays.items():
+        mine.arrays.setdefault(k, v)
+    parity.check_problem(cuda_engine, mine, check_tangent=True)
+    obj = pkg.Objective(cuda_engine, mine, lanes=16)
+    obj.parameterize(trxfile.tiles_to_wide(mine.view("prog").parameters, parity.tile_arrays(ref, "params")))
+    solver = pkg.GradientDescentSolver(obj, learning_rate=float(ref.arrays["gd/learning_rate"][0]))
+    solver.gather(ref.arrays["x"])
+    parity.check_gd_iterates(lambda: (solver.step(), solver.scatter()), ref)
