@@ -97,7 +97,7 @@ static void registerShapes(dexsyn::Model &model) {
     model.collision_pairs.push_back(cp);
   };
   const int n_ee = (int)model.end_effectors.size();
-  for (int e = 0; e < n_ee; e++) pair(e, h_ee[e], model.object_joint, h_obj);
+  for (int e = 0; e < n_ee - (model.floor_pair ? 0 : 1); e++) pair(e, h_ee[e], model.object_joint, h_obj);
   for (int e = 0; e + 2 < n_ee; e++) pair(e, h_ee[e], model.end_effectors[e + 1], h_ee[e + 1]);
 }
 
@@ -314,6 +314,7 @@ static void recordDexSyn(GradientSet &gs, const std::map<std::string, std::strin
   mo.dropout = getI(kv, "dropout", 0) != 0;
   mo.collision = getI(kv, "collision", 0) != 0;
   mo.friction = getI(kv, "friction", 0) != 0;
+  mo.floor_pair = getI(kv, "floor_pair", 1) != 0;
   mo.seed = (uint64_t)getI(kv, "seed", 20211227);
   int frames = (int)getI(kv, "frames", 4);
   int outer = (int)getI(kv, "outer", 1);

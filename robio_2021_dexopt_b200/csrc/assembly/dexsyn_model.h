@@ -72,6 +72,7 @@ struct Model {
   // floor against the object, and neighbouring finger tips against each other.  Filled by registerShapes().
   std::vector<CollisionPair> collision_pairs;
   bool wants_collision_pairs = false;
+  bool floor_pair = true;
   bool friction_cones = false;  // collision_project_2 normals + friction-cone penalties (dexlearn.h:219-233,324-362)
   // dynamic body of the object (physics5.h:78-96)
   double body_center[3] = {0, 0, 0};
@@ -156,6 +157,9 @@ struct ModelOptions {
   bool dropout = false;
   bool collision = false;  // collision penalties between registered link shapes (dexlearn.h:66-131)
   bool friction = false;   // friction-cone penalties from collision_project_2 normals (dexlearn.h:324-362)
+  bool floor_pair = true;  // collision=1: also test the floor against the object.  The object starts resting on the
+                           // floor, face on face: the closest points of two parallel faces are not unique, so two
+                           // correct implementations may report different witnesses (tests use 0 for exact parity)
   uint64_t seed = 20211227;
 };
 
@@ -186,6 +190,7 @@ inline Model makeModel(const ModelOptions &opt) {
   m.dropout = opt.dropout;
   m.friction_cones = opt.friction;
   m.wants_collision_pairs = opt.collision;
+  m.floor_pair = opt.floor_pair;
 
   int base = addJoint(m, rng, -1, JOINT_FIXED, "base", false, false);
   std::vector<int> tips;

@@ -47,6 +47,7 @@ inline ProblemOptions parseProblemOptions(const char *options) {
   po.model.dropout = getI("dropout", 0) != 0;
   po.model.collision = getI("collision", 0) != 0;
   po.model.friction = getI("friction", 0) != 0;
+  po.model.floor_pair = getI("floor_pair", 1) != 0;
   po.model.seed = (uint64_t)getI("seed", 20211227);
   po.frames = (int)getI("frames", 4);
   po.outer = (int)getI("outer", 1);

@@ -50,7 +50,8 @@ static void registerShapes(dexsyn::Model &model) {
     model.collision_pairs.push_back(cp);
   };
   const int n_ee = (int)model.end_effectors.size();
-  for (int e = 0; e < n_ee; e++) pair(e, model.ee_shapes[e], model.object_joint, model.object_shape);
+  // (the floor is the last end effector)
+  for (int e = 0; e < n_ee - (model.floor_pair ? 0 : 1); e++) pair(e, model.ee_shapes[e], model.object_joint, model.object_shape);
   for (int e = 0; e + 2 < n_ee; e++) pair(e, model.ee_shapes[e], model.end_effectors[e + 1], model.ee_shapes[e + 1]);
 }
 
@@ -94,6 +95,7 @@ int trx_dexsyn_build(const char *options, uint8_t **out, uint64_t *out_bytes) {
     mo.dropout = getI("dropout", 0) != 0;
     mo.collision = getI("collision", 0) != 0;
     mo.friction = getI("friction", 0) != 0;
+    mo.floor_pair = getI("floor_pair", 1) != 0;
     mo.seed = (uint64_t)getI("seed", 20211227);
     int frames = (int)getI("frames", 4);
     int outer = (int)getI("outer", 1);

@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       if (lane32 < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + 32 * lane32));
       else if (lane32 < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(next + 256 + 64 * (lane32 - 4)));
     }
-    if (sub < nsub) trxvm::exec(op, c);
+    if (sub < nsub) trxvm::exec<false>(op, c);  // (collision operators: staged kernel only, see executeImpl)
     __syncwarp();  // chain-scheduled streams: the next record of this warp may read what this one wrote
     if (rec_trace) {
       // development aid: per-record breakdown {start, argument words arrived, done, opcode}; the stores of
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 // ahead of the interpreter.  Header and argument words then cost a shared-memory read instead of two
 // dependent L2 round trips per record; the only global latency left on a record's critical path is its
 // operands.
-template <int kMaxWarps, int kPage, int kPages, bool kTrace>
+template <int kMaxWarps, int kPage, int kPages, bool kTrace, bool kCollision>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     trx_vm_staged_kernel(const uint32_t *__restrict__ stream, const uint64_t *__restrict__ stream_begin, double *mem,
                          uint64_t tile_stride, long long *trace) {
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       c.nargs = nargs;
       c.preloaded = false;
       c.a = pc + 1 + lane32;
-      if (lane32 < nsub) trxvm::exec(op, c);
+      if (lane32 < nsub) trxvm::exec<kCollision>(op, c);
       pos += 1 + nargs * 32;
     } else {
       trxvm::CtxT<4, 8, true> c;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
       c.preloaded = false;
       c.lo = lane32 & 7;
       c.a = pc + 1 + (lane32 >> 3);
-      if ((lane32 >> 3) < nsub) trxvm::exec(op, c);
+      if ((lane32 >> 3) < nsub) trxvm::exec<kCollision>(op, c);
       pos += 1 + nargs * 4;
     }
     if (rec_trace) {
@@ -1281,17 +1281,24 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
       constexpr int kPages = 4;
       const size_t bytes = (size_t)kStagedWarps * 512 * kPages * sizeof(uint32_t);
       if (firstUseOnDevice(m->device, 1)) {
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TRX_CUDA(cudaFuncSetAttribute(trx_vm_staged_kernel<kStagedWarps, 512, kPages, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
       }
       const size_t smem_bytes = (size_t)W * 512 * kPages * sizeof(uint32_t);
-      if (g_trace)  // development aid (trx_debug_trace): the instrumented instantiation
-        trx_vm_staged_kernel<kStagedWarps, 512, kPages, true><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+      if (p->low.uses_shapes)  // the instantiation with the collision operators (GJK / EPA calls, 7 KB stack frame)
+        trx_vm_staged_kernel<kStagedWarps, 512, kPages, false, true><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+            p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, nullptr);
+      else if (g_trace)  // development aid (trx_debug_trace): the instrumented instantiation
+        trx_vm_staged_kernel<kStagedWarps, 512, kPages, true, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, g_trace);
       else
-        trx_vm_staged_kernel<kStagedWarps, 512, kPages, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
+        trx_vm_staged_kernel<kStagedWarps, 512, kPages, false, false><<<(unsigned)m->n_tiles, W * 32, smem_bytes, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, nullptr);
     } else {
+      if (p->low.uses_shapes)
+        return fail(TRX_ERR_UNSUPPORTED, "collision operators run in the staged interpreter only (TRX_STAGED=0 or a "
+                                         "non-default page size selects a development kernel without them)");
       if (p->low.global_pool)
         trx_vm_kernel<16, false, true, true><<<(unsigned)m->n_tiles, W * 32, 0, stream>>>(
             p->d_stream, p->d_stream_begin, m->d_mem, m->tile_stride, 0, g_trace, p->d_pool, 0, 0, p->low.page_words);

@@ -278,7 +278,10 @@ TRX_HD constexpr int sigArgCount(const char *sig) {
 
 // One instruction.  `opcode` is warp-uniform, so the switch does not diverge.  The argument words
 // are fetched first, as many as the operator's signature names.
-template <class C>
+// kWithCollision = false compiles the collision operators' bodies out: their GJK / EPA routines are real calls with
+// a 7 KB stack frame, which costs every launch of a kernel that contains them local memory and registers around the
+// call sites -- programs without those operators run an instantiation without them (trx_engine.cu executeImpl).
+template <bool kWithCollision = true, class C>
 TRX_HD void exec(uint32_t opcode, C &c) {
   switch (opcode) {
 #define TRX_OP(ENUM, NAME, MODE, SIG, ...)        \

@@ -28,4 +28,7 @@ $R record $G/sq_small.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=
 # reference operators, gradients and engine; the Bullet call inside them answered through the hook of
 # oracle/ref_build/shim/tractor_collision/collision_decl.h by csrc/collision/trx_collide.h (parity of that query unpinned)
 $R record $G/dexsyn_collision.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 collision=1 friction=1 gd_steps=10 programs=0 gd_keep=last
+# ... and without the floor / object pair (the object rests on the floor face to face: non-unique witnesses), for exact
+# parity of the device, whose rounding differs from the host's
+$R record $G/dexsyn_collision_nofloor.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 collision=1 friction=1 floor_pair=0 gd_steps=10 programs=0 gd_keep=last
 ls -la $G
