@@ -89,6 +89,15 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, b
   }
   const uint64_t G = prep.memory_size;  // gradient slot offset
 
+  // The reference converts every port to its gradient type (Pose -> Twist, Quaternion -> Vector3,
+  // gradients.cpp:72-86); here ports are copied with their value layout, which is the same thing for scalars and
+  // vectors -- the only port types the product's recorder creates.  Refuse the others instead of mis-sizing them.
+  for (auto *ports : {&src.inputs, &src.outputs})
+    for (auto &p : *ports) {
+      const uint32_t comps = p.size / (8 * (p.lanes ? p.lanes : 1));
+      if (comps == 7 || comps == 4)
+        throw std::runtime_error("pose- or quaternion-typed input / output ports are not supported by this gradient builder");
+    }
   // ---- bprop (gradients.cpp:67-234)
   {
     for (auto p : src.inputs) {
@@ -156,8 +165,13 @@ inline void buildGradients(const trxfile::Program &src, GradientPrograms &out, b
             // accumulated in place by the operator; zero it once before its first use, and make every
             // later element-wise writer accumulate instead of overwrite
             bool first = true;
-            for (uint32_t off = 0; off < op.args[k].size; off += eb)
-              if (written.count(r.args[k] + off)) first = false;
+            uint32_t n_written = 0, n_elems = 0;
+            for (uint32_t off = 0; off < op.args[k].size; off += eb, n_elems++)
+              if (written.count(r.args[k] + off)) first = false, n_written++;
+            // all or nothing: a block some of whose elements already have a writer would keep stale values in the
+            // others (the zero prologue below skips outputs)
+            if (n_written != 0 && n_written != n_elems)
+              throw std::runtime_error("accumulated gradient block partly written before its first block use");
             if (first) {
               RInst z;
               z.op = internBlockOp(bprop, index, "x_zero_block_d", {op.args[k].size});

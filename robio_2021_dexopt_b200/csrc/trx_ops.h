@@ -67,7 +67,11 @@ inline const std::vector<OpSig> &opTable() {
         op.cost += (unsigned)n;
         if (a.kind >= ARG_TB) op.coop = true;
       }
-      const char *prefix = op.mode == 'P' ? "prepare_" : op.mode == 'F' ? "forward_" : op.mode == 'R' ? "reverse_" : "";
+      // C P F R, and the constraint modes J I K D X Y Z (vm_ops.def, constraint operators)
+      const char *prefix = op.mode == 'P' ? "prepare_" : op.mode == 'F' ? "forward_" : op.mode == 'R' ? "reverse_"
+                           : op.mode == 'J' ? "project_" : op.mode == 'I' ? "barrier_init_" : op.mode == 'K' ? "barrier_step_"
+                           : op.mode == 'D' ? "barrier_diagonal_" : op.mode == 'X' ? "penalty_init_"
+                           : op.mode == 'Y' ? "penalty_step_" : op.mode == 'Z' ? "penalty_diagonal_" : "";
       op.tape_name = std::string(prefix) + op.base;
     }
     return t;
