@@ -26,6 +26,8 @@
 #include <thread>
 
 #include "ref_backend.h"
+#include <tractor/core/constraints.h>
+#include <tractor/core/gradients.h>
 #include "../../robio_2021_dexopt_b200/csrc/assembly/dexsyn_assemble.h"
 
 #include "../../robio_2021_dexopt_b200/csrc/collision/trx_shape_table.h"
@@ -159,6 +161,137 @@ static int cmdRegistry(const std::string &path) {
 
 static bool endsWith(const std::string &s, const std::string &suffix) {
   return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
+// Every registered operator whose name contains "constraint" (core/constraints.h, geometry/ops.h:998-1130), in every
+// mode -- compute, prepare, forward, reverse, project, barrier_init / _step / _diagonal, penalty_* -- as its own
+// single-instruction program: random inputs, the reference SimpleEngine's outputs.
+static int cmdConstraintTests(const std::string &path, const std::map<std::string, std::string> &kv) {
+  std::string suffix = "_" + getS(kv, "suffix", "8d");
+  dexsyn::Rng rng((uint64_t)getI(kv, "seed", 11));
+  auto ops = tractor::Operator::all();
+  std::sort(ops.begin(), ops.end(),
+            [](const tractor::Operator *a, const tractor::Operator *b) { return a->name() < b->name(); });
+  trxfile::Bundle bundle;
+  std::string listing;
+  for (auto *op : ops) {
+    const std::string &n = op->name();
+    if (n.find("constraint") == std::string::npos || !endsWith(n, suffix)) continue;
+    bool has_output = false;
+    for (auto &arg : op->arguments()) has_output |= !arg.isInput();
+    if (!has_output) continue;  // prepare rules of constraints save nothing
+    tractor::Program prog;
+    std::vector<tractor::Program::Instruction> insts;
+    // every argument in its own 512-byte cell: the reference's quaternion / vector3 barrier rules index six
+    // components of three-component arguments (geometry/ops.h:1076-1081,1106-1125); the padding keeps those stray
+    // accesses away from the neighbouring arguments, so the in-range components are well defined
+    size_t addr = 512;
+    insts.push_back((uintptr_t)op);
+    size_t in_off = 0, out_off = 0;
+    for (auto &arg : op->arguments()) {
+      insts.push_back(addr);
+      if (arg.isInput()) {
+        prog.addInput(tractor::Program::Input(arg.typeInfo(), addr, in_off, 0));
+        in_off += arg.size();
+      } else {
+        prog.addOutput(tractor::Program::Output(arg.typeInfo(), addr, out_off, 0));
+        out_off += arg.size();
+      }
+      addr += 512;
+    }
+    prog.updateMemorySize(addr + 512);
+    prog.setInstructions(insts);
+    size_t nx = portElements(prog.inputs());
+    std::vector<double> x(nx), y;
+    for (auto &v : x) v = rng.uniform(-1, 1);
+    auto engine = std::make_shared<tractor::SimpleEngine>();
+    auto memory = engine->createMemory();
+    auto x_prog = engine->compile(prog);
+    x_prog->run(x, memory, y);
+    std::string prefix = "op/" + n + "/";
+    bundle.programs.emplace_back(prefix + "prog", convertProgram(prog));
+    bundle.arrays.emplace_back(prefix + "x", x);
+    bundle.arrays.emplace_back(prefix + "y", y);
+    listing += n + "\n";
+  }
+  bundle.texts.emplace_back("ops", listing);
+  trxfile::writeBundle(bundle, path);
+  return 0;
+}
+
+// A small bounded least-squares tape whose variables carry constraints, as robot/jointtypes.h:105-119 records them
+// for joint variables: goals (w_i - target_i per lane), goal(range_constraint(w, lo, hi)) /
+// goal(trust_region_constraint(w, tr)) / goal(range_trust_region_constraint(w, lo, hi, tr)).  The reference's
+// buildGradients + buildConstraints (gradients.cpp:22-407,764-997) derive the programs SolverBase compiles
+// (solvers/base.h:117-137); the reference engine runs them the way solvers/ip.h:212-246,287-293,475-478 does.
+static int cmdConstrained(const std::string &path, const std::map<std::string, std::string> &kv) {
+  const int n = (int)getI(kv, "variables", 12);
+  dexsyn::Rng rng((uint64_t)getI(kv, "seed", 5));
+  GradientSet gs;
+  std::deque<tractor::Var<double>, tractor::AlignedStdAlloc<tractor::Var<double>>> vars;
+  std::deque<tractor::Var<Lane>, tractor::AlignedStdAlloc<tractor::Var<Lane>>> params;
+  std::vector<double> x0(n);
+  {
+    MuteCout mute;
+    gs.prog.record([&]() {
+      for (int i = 0; i < n; i++) {
+        x0[i] = rng.uniform(-0.5, 0.5);
+        vars.emplace_back(x0[i]);
+        tractor::variable(vars.back());
+        params.emplace_back(Lane(0));
+        tractor::parameter(params.back());
+        tractor::Var<Lane> wi;
+        tractor::batch(vars.back(), wi);
+        tractor::goal(tractor::sub(wi, params.back()));
+        const double lo = x0[i] - rng.uniform(0.05, 0.6), hi = x0[i] + rng.uniform(0.05, 0.6), tr = rng.uniform(0.05, 0.4);
+        if (i % 4 == 0) tractor::goal(tractor::range_constraint(vars.back(), tractor::Var<double>(lo), tractor::Var<double>(hi)));
+        else if (i % 4 == 1) tractor::goal(tractor::trust_region_constraint(vars.back(), tractor::Var<double>(tr)));
+        else if (i % 4 == 2)
+          tractor::goal(tractor::range_trust_region_constraint(vars.back(), tractor::Var<double>(lo), tractor::Var<double>(hi),
+                                                               tractor::Var<double>(tr)));
+        // (i % 4 == 3: an unconstrained variable -- buildConstraints passes it through: move / zero)
+      }
+    });
+  }
+  gs.build();
+  tractor::Program proj, b_init, b_step, b_diag, p_init, p_step, p_diag;
+  tractor::buildConstraints(gs.prog, gs.fprop, gs.bprop, gs.hprop, tractor::TypeInfo::get<double>(), &proj, &b_init, &b_step,
+                            &b_diag, &p_init, &p_step, &p_diag);
+  trxfile::Bundle bundle;
+  gs.addTo(bundle);
+  bundle.programs.emplace_back("project", convertProgram(proj));
+  bundle.programs.emplace_back("barrier_init", convertProgram(b_init));
+  bundle.programs.emplace_back("barrier_step", convertProgram(b_step));
+  bundle.programs.emplace_back("barrier_diagonal", convertProgram(b_diag));
+  auto engine = std::make_shared<tractor::SimpleEngine>();
+  auto memory = engine->createMemory();
+  auto x_prog = engine->compile(gs.prog);
+  auto x_proj = engine->compile(proj), x_bi = engine->compile(b_init), x_bs = engine->compile(b_step),
+       x_bd = engine->compile(b_diag);
+  std::vector<double> par(portElements(gs.prog.parameters())), r, step(n), step2(n), padding(1, 0.05), y;
+  for (auto &v : par) v = rng.uniform(-0.5, 0.5);
+  for (auto &v : step) v = rng.uniform(-0.7, 0.7);  // some steps leave their ranges
+  for (auto &v : step2) v = rng.uniform(-0.2, 0.2);
+  x_prog->parameterVector(par, memory);
+  x_prog->run(x0, memory, r);
+  bundle.arrays.emplace_back("x", x0);
+  bundle.arrays.emplace_back("tile0/params", par);
+  bundle.arrays.emplace_back("tile0/r", r);
+  bundle.arrays.emplace_back("step", step);
+  bundle.arrays.emplace_back("step2", step2);
+  bundle.arrays.emplace_back("padding", padding);
+  x_proj->parameterVector(padding, memory);
+  x_proj->run(step, memory, y);
+  bundle.arrays.emplace_back("project/y", y);
+  x_bi->run(step2, memory, y);
+  bundle.arrays.emplace_back("barrier_init/y", y);
+  x_bs->run(step, memory, y);
+  bundle.arrays.emplace_back("barrier_step/y", y);
+  x_bd->execute(memory);
+  x_bd->outputVector(memory, y);
+  bundle.arrays.emplace_back("barrier_diagonal/y", y);
+  trxfile::writeBundle(bundle, path);
+  return 0;
 }
 
 static int cmdOpTests(const std::string &path, const std::map<std::string, std::string> &kv) {
@@ -670,6 +803,8 @@ int main(int argc, char **argv) {
     if (argc < 2) throw std::runtime_error("usage: ref_tool registry|optests|record|bench ...");
     std::string cmd = argv[1];
     if (cmd == "registry") return cmdRegistry(argv[2]);
+    if (cmd == "constraint_tests") return cmdConstraintTests(argv[2], parseArgs(argc, argv, 3));
+    if (cmd == "constrained") return cmdConstrained(argv[2], parseArgs(argc, argv, 3));
     if (cmd == "optests") return cmdOpTests(argv[2], parseArgs(argc, argv, 3));
     if (cmd == "record") return cmdRecord(argv[2], parseArgs(argc, argv, 3));
     if (cmd == "bench") return cmdBench(parseArgs(argc, argv, 2));

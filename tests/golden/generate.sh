@@ -31,4 +31,9 @@ $R record $G/dexsyn_collision.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extr
 # ... and without the floor / object pair (the object rests on the floor face to face: non-unique witnesses), for exact
 # parity of the device, whose rounding differs from the host's
 $R record $G/dexsyn_collision_nofloor.trxb problem=dexsyn frames=3 hidden=4 tiles=2 extra_fixed=4 collision=1 friction=1 floor_pair=0 gd_steps=10 programs=0 gd_keep=last
+# constraint operators in every mode (single instructions), and the project / barrier programs buildConstraints derives
+# for a small bounded least-squares tape (core/constraints.h, gradients.cpp:764-997)
+$R constraint_tests $G/constraint_ops_8d.trxb suffix=8d
+$R constraint_tests $G/constraint_ops_d.trxb suffix=d
+$R constrained $G/constrained_small.trxb
 ls -la $G
