@@ -175,7 +175,8 @@ void trx_set_random_seed(uint64_t seed);
  *   kind TRX_SHAPE_CYLINDER:   radius, length, axis z, centred         (shape.h:139-171)
  *   kind TRX_SHAPE_POLYHEDRON: points (support mapping), planes (nx ny nz offset, inside <= 0; project());
  *                              center = mean of the points             (shape.h:196-222,327-346)
- * A pair names the two shapes of one collision_axes instruction.  Handles stay valid until trx_collision_clear. */
+ * A pair names the two shapes of one collision_axes instruction.  Handles stay valid until trx_collision_clear;
+ * a program created before a clear refuses to execute afterwards (TRX_ERR_INVALID) instead of reading dead records. */
 enum { TRX_SHAPE_SPHERE = 1, TRX_SHAPE_CYLINDER = 2, TRX_SHAPE_POLYHEDRON = 3 };
 typedef struct trx_shape_desc {
   int kind;

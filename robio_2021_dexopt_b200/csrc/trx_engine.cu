@@ -780,6 +780,7 @@ struct trx_program {
   uint32_t n_elems[3] = {0, 0, 0};
   int scalar_inputs = TRX_SCALAR_SHARED, scalar_outputs = TRX_SCALAR_SHARED;
   bool has_scalar_outputs = false;  // any output port of scalar type (one value for all lanes)
+  uint64_t shape_generation = 0;    // collision shape table the program's handles were checked against
   const trx::PortLayout &layout(int which) const {
     return which == TRX_BUF_INPUT ? low.inputs : which == TRX_BUF_PARAMETER ? low.parameters : low.outputs;
   }
@@ -931,7 +932,7 @@ trx_status trx_debug_trace(uint64_t n_words, long long **device_buffer) {
 static trx_status finishProgram(std::unique_ptr<trx_program> &p, int device, int scalar_in, int scalar_out,
                                 trx_program **out);
 
-static trx_status checkShapeHandles(const trxfile::Program &src);
+static trx_status checkShapeHandles(const trxfile::Program &src, uint64_t *generation);
 static trx_status createFromFile(const trxfile::Program &src, int device, int scalar_in, int scalar_out,
                                  trx_program **out, bool fold_accumulate = false) {
   if (!out) return fail(TRX_ERR_INVALID, "null output pointer");
@@ -961,7 +962,7 @@ static trx_status createFromFile(const trxfile::Program &src, int device, int sc
     return fail(unsupported ? TRX_ERR_UNSUPPORTED : TRX_ERR_INVALID, msg);
   }
   if (p->low.uses_shapes) {
-    trx_status cs = checkShapeHandles(src);
+    trx_status cs = checkShapeHandles(src, &p->shape_generation);
     if (cs != TRX_OK) return cs;
   }
   return finishProgram(p, device, scalar_in, scalar_out, out);
@@ -1159,6 +1160,7 @@ struct ShapeRegistry {
   std::mutex mu;
   trxcol::ShapeTable table;
   uint64_t version = 1;
+  uint64_t generation = 1;  // bumped by trx_collision_clear: handles of an earlier generation are dead
   struct Mirror {
     double *d = nullptr;
     uint64_t version = 0, capacity = 0;
@@ -1188,9 +1190,10 @@ static trx_status syncShapeTable(int device, cudaStream_t stream) {
   return TRX_OK;
 }
 // every uint64 constant that a collision instruction reads must be a registered handle of the right kind
-static trx_status checkShapeHandles(const trxfile::Program &src) {
+static trx_status checkShapeHandles(const trxfile::Program &src, uint64_t *generation) {
   ShapeRegistry &R = shapeRegistry();
   std::lock_guard<std::mutex> lock(R.mu);
+  *generation = R.generation;
   std::unordered_map<uint64_t, uint64_t> const_at;  // address -> bits
   for (auto &c : src.constants)
     if (c.size == 8 && c.offset + 8 <= src.const_data.size()) {
@@ -1252,6 +1255,13 @@ static trx_status executeImpl(const trx_program *p, trx_memory *m, void *stream_
     TRX_CUDA(cudaMemcpyToSymbolAsync(trxvm::g_rng_dev, &st, sizeof(st), 0, cudaMemcpyHostToDevice, stream));
   }
   if (p->low.uses_shapes) {
+    {
+      ShapeRegistry &R = shapeRegistry();
+      std::lock_guard<std::mutex> lock(R.mu);
+      if (p->shape_generation != R.generation)
+        return fail(TRX_ERR_INVALID, "the collision shape table was cleared after this program was created: its "
+                                     "shape handles are dead");
+    }
     trx_status cs = syncShapeTable(m->device, stream);
     if (cs != TRX_OK) return cs;
   }
@@ -1672,6 +1682,7 @@ void trx_collision_clear(void) {
   std::lock_guard<std::mutex> lock(R.mu);
   R.table.clear();
   R.version++;
+  R.generation++;
   trxvm::shapeHeapHost() = R.table.heap.data();
 }
 

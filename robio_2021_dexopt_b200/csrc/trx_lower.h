@@ -236,6 +236,32 @@ inline void lowerProgram(const trxfile::Program &src, const LowerOptions &opt, L
   }
   out.n_instructions = n_decoded;
 
+  // The dense-layer kernels read their weight and bias blocks through the read-only data path (__ldg): that is only
+  // valid while no EARLIER instruction of the same launch has written those slots (a later writer -- the adjoint of
+  // an hprop program accumulating into the slots its tangent sweep read -- is ordered behind the read by a level
+  // barrier).  Weights are input ports in every tape the recorders produce; a program that computes them first is
+  // refused rather than served stale values.
+  {
+    std::vector<std::pair<uint64_t, uint64_t>> written;  // [begin, end) of the output arguments so far (program order)
+    for (auto &in : insts) {
+      const OpSig &sig = table[ops[in.op].opcode];
+      if (sig.coop)
+        for (size_t k = 0; k < sig.args.size(); k++) {
+          if (!sig.args[k].is_input || sig.args[k].kind != ARG_SB) continue;
+          const uint64_t a = src.code[in.code_at + k], e = a + src.ops[in.op].args[k].size;
+          for (auto &w : written)
+            if (w.first < e && w.second > a)
+              throw std::runtime_error("unsupported operator use: a dense layer's weight block is computed by the same program");
+        }
+      for (size_t k = 0; k < sig.args.size(); k++)
+        if (!sig.args[k].is_input) {
+          const uint64_t a = src.code[in.code_at + k];
+          // (only writers of scalar slots can alias a weight block; lane-typed outputs live elsewhere)
+          if (src.ops[in.op].args[k].lanes == 1 || sig.coop) written.push_back({a, a + src.ops[in.op].args[k].size});
+        }
+    }
+  }
+
   // ---- 2b. copy propagation and accumulate folding (see LowerOptions)
   std::vector<uint64_t> code(src.code);        // argument addresses after the rewrites
   std::vector<uint64_t> base;                  // ... after copy propagation: what the folding patterns match on

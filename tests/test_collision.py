@@ -496,6 +496,20 @@ def test_collision_objective_and_gradient_descent_on_the_device(cuda_engine, gol
 
 
 @pytest.mark.gpu
+def test_program_refuses_to_run_after_the_shape_table_was_cleared(cuda_engine):
+    import robio_2021_dexopt_b200 as pkg
+    pkg.collision.clear()
+    box = pkg.collision.polyhedron(cu.SHAPES["box"]["points"], cu.SHAPES["box"]["planes"])
+    x = cuda_engine.compile(one_instruction("collision_project_2_8d", "iT3 iU1 oT3 oT1", box.handle))
+    mem = cuda_engine.createMemory(8)
+    x.run(np.zeros(24), mem)
+    pkg.collision.clear()
+    with pytest.raises(pkg.TrxError) as e:
+        x.run(np.zeros(24), mem)
+    assert e.value.status == -1
+
+
+@pytest.mark.gpu
 def test_rollout_objective_refuses_collision_problems(cuda_engine):
     """the re-rolled rollout kernel has no collision phases: it must say so instead of dropping the penalties"""
     import robio_2021_dexopt_b200 as pkg
