@@ -3,6 +3,7 @@
 // through tractor::CudaEngine (integration/cuda_engine.h -> include/trx_b200.h -> libtrx_b200.so),
 // compared element by element.  Runs on the GPU box (tests/test_cuda_engine.py).  TEST INFRASTRUCTURE.
 #include "ref_backend.h"
+#include <tractor/core/gradients.h>
 #include "../../integration/cuda_engine.h"
 #include "../../robio_2021_dexopt_b200/csrc/assembly/dexsyn_assemble.h"
 
@@ -61,6 +62,48 @@ int main(int argc, char **argv) {
     std::vector<double> r0, g0, h0, r1, g1, h1;
     runAll(std::make_shared<tractor::SimpleEngine>(), r0, g0, h0);
     runAll(std::make_shared<tractor::CudaEngine>(0), r1, g1, h1);
+    // the other executables SolverBase compiles for every solver (solvers/base.h:112-137): accu, and the seven
+    // programs of buildConstraints -- for a tape without constraint operators project is a move per variable, the
+    // barrier programs zeros, the penalty programs empty
+    tractor::Program proj, b_init, b_step, b_diag, p_init, p_step, p_diag;
+    tractor::buildConstraints(gs.prog, gs.fprop, gs.bprop, gs.hprop, tractor::TypeInfo::get<double>(), &proj, &b_init,
+                              &b_step, &b_diag, &p_init, &p_step, &p_diag);
+    auto runRest = [&](const std::shared_ptr<tractor::Engine> &engine, std::vector<double> &out) {
+      auto memory = engine->createMemory();
+      auto x_prog = engine->compile(gs.prog);
+      auto x_accu = engine->compile(gs.accu);
+      auto x_proj = engine->compile(proj), x_bi = engine->compile(b_init), x_bs = engine->compile(b_step),
+           x_bd = engine->compile(b_diag), x_pi = engine->compile(p_init), x_ps = engine->compile(p_step),
+           x_pd = engine->compile(p_diag);
+      std::vector<double> r, y, step(x.size()), xd(2 * x.size());
+      for (size_t i = 0; i < step.size(); i++) step[i] = 0.02 * std::cos(0.11 * (double)i);
+      x_prog->parameterVector(params, memory);
+      x_prog->run(x, memory, r);
+      out.clear();
+      // accumulate: x (+) step   (solvers/base.h:158-165: inputs x then the step)
+      for (size_t i = 0; i < x.size(); i++) xd[i] = x[i], xd[x.size() + i] = step[i];
+      x_accu->run(xd, memory, y);
+      out.insert(out.end(), y.begin(), y.end());
+      x_proj->parameterVector(std::vector<double>(1, 0.1), memory);
+      x_proj->run(step, memory, y);
+      out.insert(out.end(), y.begin(), y.end());
+      x_bi->run(step, memory, y);
+      out.insert(out.end(), y.begin(), y.end());
+      x_bs->run(step, memory, y);
+      out.insert(out.end(), y.begin(), y.end());
+      x_bd->execute(memory);
+      x_bd->outputVector(memory, y);
+      out.insert(out.end(), y.begin(), y.end());
+      x_pi->execute(memory);
+      x_ps->execute(memory);
+      x_pd->execute(memory);
+    };
+    std::vector<double> rest0, rest1;
+    runRest(std::make_shared<tractor::SimpleEngine>(), rest0);
+    runRest(std::make_shared<tractor::CudaEngine>(0), rest1);
+    const double erest = maxRelErr(rest1, rest0);
+    std::printf("{\"solverbase_executables\": 13, \"values\": %zu, \"err_rest\": %.3g}\n", rest0.size(), erest);
+    if (!(erest < 1e-12)) return 3;
     double er = maxRelErr(r1, r0), eg = maxRelErr(g1, g0), eh = maxRelErr(h1, h0);
     std::printf("{\"residuals\": %zu, \"gradient\": %zu, \"err_r\": %.3g, \"err_g\": %.3g, \"err_h\": %.3g}\n", r0.size(),
                 g0.size(), er, eg, eh);

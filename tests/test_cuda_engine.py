@@ -261,9 +261,13 @@ def test_reference_code_runs_on_cuda_engine_through_the_tractor_interface():
         pytest.skip("oracle/_ref/ref_cuda_engine_test is not built (needs the reference sources)")
     out = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    res = json.loads(out.stdout.strip().splitlines()[-1])
+    lines = out.stdout.strip().splitlines()
+    res = json.loads(lines[-1])
     assert res["err_r"] < 1e-9 and res["err_g"] < 1e-9 and res["err_h"] < 1e-9
     assert res["residuals"] > 1000
+    # all thirteen executables SolverBase compiles (solvers/base.h:112-137), accu and buildConstraints' seven included
+    rest = json.loads(lines[-2])
+    assert rest["solverbase_executables"] == 13 and rest["err_rest"] < 1e-12 and rest["values"] > 1000
 
 
 @pytest.mark.gpu
