@@ -35,6 +35,9 @@ LANES_PER_GPU = int(os.environ.get("BENCH_LANES", 1024))
 TOTAL_ROLLOUTS = int(os.environ.get("BENCH_TOTAL_ROLLOUTS", 0))  # > 0: strong scaling, rollouts split over the ranks
 KIND = os.environ.get("BENCH_KIND", "handarm")
 HIDDEN = int(os.environ.get("BENCH_HIDDEN", 64))
+# initial policy weights N(0, WSTD^2): DenseLayer's default stdev (dexopt/src/neural.h:134-136).  (With 0.1 the
+# 256-frame rollout leaves every physical regime and its gradient overflows fp64 -- same time per evaluation, no meaning.)
+WSTD = float(os.environ.get("BENCH_WSTD", 0.001))
 ENGINE = os.environ.get("BENCH_ENGINE", "rollout")  # rollout | tape
 FUSE_DENSE = int(os.environ.get("BENCH_FUSE_DENSE", 1))  # tape engine: dense layers as block instructions
 MAX_DEVICE_BYTES = int(float(os.environ.get("BENCH_MAX_DEVICE_GB", 150)) * 1e9)
@@ -120,7 +123,7 @@ def reference_cpu(threads, frames, seconds, repeats=1, engine="simple"):
     when every thread has built its runner; the median of `repeats` windows of `seconds` is reported."""
     if not os.path.exists(REF_TOOL):
         return None
-    out = subprocess.run([REF_TOOL, "bench", "kind=" + KIND, "hidden=%d" % HIDDEN, "frames=%d" % frames,
+    out = subprocess.run([REF_TOOL, "bench", "kind=" + KIND, "hidden=%d" % HIDDEN, "wstd=%g" % WSTD, "frames=%d" % frames,
                           "threads=%d" % threads, "seconds=%g" % seconds, "repeats=%d" % repeats, "engine=" + engine],
                          capture_output=True, text=True)
     for line in out.stdout.splitlines():
@@ -210,7 +213,7 @@ def parity_check(pkg, engine_obj, np):
     frames = 16
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "slice.trxb")
-        subprocess.run([REF_TOOL, "record", path, "problem=dexsyn", "kind=" + KIND, "hidden=%d" % HIDDEN,
+        subprocess.run([REF_TOOL, "record", path, "problem=dexsyn", "kind=" + KIND, "hidden=%d" % HIDDEN, "wstd=%g" % WSTD,
                         "frames=%d" % frames, "tiles=2", "programs=0", "keep_dr=0"], check=True, capture_output=True)
         ref = trxfile.load(path)
     params = np.concatenate([ref.arrays["tile%d/params" % t].reshape(-1, 8) for t in range(2)], axis=1).copy()
@@ -260,7 +263,7 @@ def main():
         parity = parity_check(pkg, engine, np)
 
     t_build = time.time()
-    problem = dict(kind=KIND, hidden=HIDDEN)
+    problem = dict(kind=KIND, hidden=HIDDEN, wstd=WSTD)
     if ENGINE == "rollout":
         obj = pkg.RolloutObjective(engine, lanes, max_device_bytes=MAX_DEVICE_BYTES, scalar_rows=(rank == 0),
                                    frames=FRAMES, **problem)
@@ -369,6 +372,8 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # the objective the timed steps evaluated is a meaningful one: finite loss and gradient
+    assert np.isfinite(loss) and np.all(np.isfinite(g)), "the benchmarked objective is not finite"
     ms_per_step = ms_total / args.steps
     value = units / (ms_per_step * 1e-3)
     e2e_value = units / (e2e_s / args.steps)
@@ -421,6 +426,8 @@ def main():
             "uncounted_operators": uncounted,
         },
         "loss": loss,
+        "gradient_norm": float(np.linalg.norm(g)),
+        "policy_weight_std": WSTD,
         "setup_s": t_build,
         "chunks": n_chunks,
         "device_bytes": obj.info("device_bytes"),
