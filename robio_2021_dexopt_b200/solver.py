@@ -137,8 +137,12 @@ class RolloutObjective(Objective):
     (csrc/trx_rollout.cu).  Built from the problem description that build_dexsyn takes; per-rollout
     parameters are [3][lanes] = object start offset x, y and yaw (dexenv_grasp.h:149-165)."""
 
+    #: what a frame's checkpoint holds (include/trx_b200.h TRX_OBJECTIVE_CHECKPOINT_*): "full" = everything the
+    #: adjoint reads (default), "policy" = carried state + policy values, "state" = the carried state only
+    CHECKPOINT_FLAGS = {"full": 0, "policy": 32, "state": 16}
+
     def __init__(self, engine: CudaEngine, lanes: int, max_device_bytes: int = 0, scalar_rows: bool = True,
-                 **options):
+                 checkpoint: str = "full", **options):
         self.engine = engine
         self._h = ctypes.c_void_p()
         self.options = " ".join("%s=%s" % (k, v) for k, v in options.items())
@@ -148,7 +152,8 @@ class RolloutObjective(Objective):
         L.trx_objective_residuals.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                               ctypes.c_void_p]
         check(L.trx_objective_create_rollout(self.options.encode(), lanes, max_device_bytes, engine.device,
-                                             0 if scalar_rows else 2, ctypes.byref(self._h)))
+                                             (0 if scalar_rows else 2) | self.CHECKPOINT_FLAGS[checkpoint],
+                                             ctypes.byref(self._h)))
         self.lanes = lanes
         self.n_x = self.info("n_x")
         self._g = np.empty(self.n_x)

@@ -131,6 +131,28 @@ def test_rollout_partial_group_and_chunks(cuda_engine, emu, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("checkpoint", ["state", "policy", "full"])
+def test_rollout_checkpoint_modes_match_reference(cuda_engine, golden, checkpoint):
+    """the three checkpoint contents (TRX_OBJECTIVE_CHECKPOINT_*: the adjoint sweep recomputes the whole frame,
+    kinematics and contacts only, or nothing) against the reference's loss and gradient of the 24-frame rollout"""
+    name = "rollout_handarm_long.trxb"
+    b = golden(name)
+    opts = ru.FIXTURES[name]
+    n_tiles = len(parity.tile_arrays(b, "params"))
+    obj = _objective(cuda_engine, opts, 8 * n_tiles, checkpoint=checkpoint)
+    assert obj.info("checkpoint_mode") == {"state": 0, "policy": 1, "full": 2}[checkpoint]
+    carried = obj.info("carried_state_bytes_per_unit")
+    if checkpoint == "state":
+        assert obj.info("checkpoint_bytes_per_unit") < carried + 128  # rounded up to whole 128-byte lines
+    pw, _ = ru.wide_from_tiles(b, obj.info("n_scalar_rows"))
+    obj.parameterize(pw)
+    loss, g = obj.evaluate(b.arrays["x"])
+    want = float(b.arrays["loss_total"][0])
+    assert abs(loss - want) <= 1e-11 * abs(want), (loss, want)
+    parity.assert_close(g, b.arrays["g_total"], "gradient")
+
+
+@pytest.mark.gpu
 def test_rollout_agrees_with_tape_objective_at_the_benchmark_shape(cuda_engine):
     """BASELINE configs[2] shape (41 -> 64 -> 83, 29 controlled joints), 16 frames x 64 rollouts: the re-rolled
     kernels against the interpreted flat tape of the same problem (itself pinned to the reference)"""
