@@ -24,6 +24,16 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(L, n), "libtrx_b200.so does not export %s" % n
 
 
+def test_python_mirror_uses_the_header_flag_values():
+    """the objective flags the Python mirror passes are the enum values of include/trx_b200.h"""
+    from robio_2021_dexopt_b200.solver import RolloutObjective
+    header = open(os.path.join(ROOT, "include", "trx_b200.h")).read()
+    value = {n: int(v) for n, v in re.findall(r"\b(TRX_OBJECTIVE_[A-Z_]+)\s*=\s*(\d+)", header)}
+    assert RolloutObjective.CHECKPOINT_FLAGS == {"full": 0, "policy": value["TRX_OBJECTIVE_CHECKPOINT_POLICY"],
+                                                 "state": value["TRX_OBJECTIVE_CHECKPOINT_STATE"]}
+    assert value["TRX_OBJECTIVE_NO_SCALAR_ROWS"] == 2  # RolloutObjective(scalar_rows=False)
+
+
 def test_operator_vocabulary_matches_reference_registry():
     """every device operator's argument layout equals what Operator::arguments() reports
     (tests/golden/ref_registry.txt, dumped from the reference's registry)"""
