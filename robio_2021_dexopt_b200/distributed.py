@@ -45,14 +45,6 @@ def shard_wide_parameters(ports, wide: np.ndarray, total_lanes: int, first_lane:
     return np.concatenate(out) if out else np.zeros(0)
 
 
-def scalar_row_correction(loss_scalar_rows: float, g_scalar_rows: np.ndarray, rank: int):
-    """what a rank subtracts from its local {loss, gradient} so that lane-independent residual rows are
-    counted once over the whole job (rank 0 keeps them)"""
-    if rank == 0:
-        return 0.0, np.zeros_like(g_scalar_rows)
-    return loss_scalar_rows, g_scalar_rows
-
-
 def allreduce_loss_gradient(buffer, group=None):
     """in-place sum of a {loss, gradient} tensor over all ranks through torch.distributed: the host-side
     equivalent of what an objective with a Communicator does on the device (CPU tests, gloo)"""
