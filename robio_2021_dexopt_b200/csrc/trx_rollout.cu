@@ -177,9 +177,13 @@ constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one bo
 //                  last layer per helper warp, over all frames and groups of the CTA) plus the bias gradients
 //                  while the main warps go on with the adjoint of the frame.
 // The two sides meet at the full barriers A..G of a step; everything else synchronises the main warps only.
-template <int NW, int U1, int UL>
+// kPlain: the evaluation stores no residual vector and takes no adjoint seeds (loss and g = J^T r only -- the solver
+// steps): compiled without the residual-row addressing of the general form
+template <int NW, int U1, int UL, bool kPlain>
 __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
     trx_rollout_kernel(const __grid_constant__ KHeader hdr, const __grid_constant__ KArgs a) {
+  double *const a_r_out = kPlain ? nullptr : a.r_out;
+  const double *const a_seed = kPlain ? nullptr : a.seed;
   extern __shared__ double sm[];
   const int32_t *H = hdr.v;
   constexpr int NH = kHelperWarps, NHD = kDwWarps, NTM = NW * 32, NTH = NH * 32, NTD = NHD * 32, MAXT = U1 + UL;
@@ -502,9 +506,9 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
     const long rollout = a.first + local;
     double *ckpt = a.ckpt + (size_t)local * T * CKX;
     // element (row, g) of the group's residual rows / seeds at [row * R + g]
-    double *grp_r = a.r_out ? a.r_out + H[H_NSCALAR] + a.first + grp_first : nullptr;
-    const double *grp_seed = a.seed ? a.seed + H[H_NSCALAR] + a.first + grp_first : nullptr;
-    c.r_out = (a.r_out && active) ? a.r_out + H[H_NSCALAR] + rollout : nullptr;
+    double *grp_r = a_r_out ? a_r_out + H[H_NSCALAR] + a.first + grp_first : nullptr;
+    const double *grp_seed = a_seed ? a_seed + H[H_NSCALAR] + a.first + grp_first : nullptr;
+    c.r_out = (a_r_out && active) ? a_r_out + H[H_NSCALAR] + rollout : nullptr;
     c.seed = nullptr;
     barAll();  // the group starts: everybody is done with the previous one
     if (!active) {
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         if (active) phaseTerminal(c, slot, loss);
         if (!a.want_grad) break;
         c.r_out = nullptr;
-        c.seed = (a.seed && active) ? a.seed + H[H_NSCALAR] + rollout : nullptr;
+        c.seed = (a_seed && active) ? a_seed + H[H_NSCALAR] + rollout : nullptr;
         if (active) {
           bphaseInit(c, slot);
           if (mode != 2) {
@@ -784,9 +788,9 @@ namespace {
 typedef void (*KernelFn)(const KHeader, const KArgs);
 struct Variant {
   int nw, u1, ul;  // rollouts per CTA, dW tiles per warp of the first / last layer
-  KernelFn fn;
+  KernelFn fn, fn_plain;  // general form; loss and g = J^T r only
 };
-#define RL_VARIANT(NW, U1, UL) {NW, U1, UL, trx_rollout_kernel<NW, U1, UL>}
+#define RL_VARIANT(NW, U1, UL) {NW, U1, UL, trx_rollout_kernel<NW, U1, UL, false>, trx_rollout_kernel<NW, U1, UL, true>}
 // smallest first: (2, 7) one-layer and narrow policies, (7, 13) the 41 -> 64 -> 83 policy of the benchmark (20 tiles
 // = 80 of the 128 registers a thread of a 16-warp CTA can have), 4 rollouts per CTA when 8 regions do not fit the
 // shared memory.  Wider policies have no re-rolled form here (TRX_ERR_UNSUPPORTED: use the tape objective).
@@ -906,6 +910,7 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   ro->u1 = pick->u1;
   ro->ul = pick->ul;
   RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
+  RL_CUDA(cudaFuncSetAttribute(pick->fn_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
 
   // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
   // what a checkpoint holds beyond the carried state: the more, the less the adjoint sweep
@@ -1005,7 +1010,7 @@ trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out,
   RL_CUDA(cudaSetDevice(ro->device));
   KernelFn fn = nullptr;
   for (const Variant &v : kVariants)
-    if (v.nw == ro->nw && v.u1 == ro->u1 && v.ul == ro->ul) fn = v.fn;
+    if (v.nw == ro->nw && v.u1 == ro->u1 && v.ul == ro->ul) fn = (d_r || d_seed) ? v.fn : v.fn_plain;
   KArgs a = ro->args;
   a.x = d_x;
   a.r_out = d_r;
