@@ -179,7 +179,8 @@ constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one bo
 // The two sides meet at the full barriers A..G of a step; everything else synchronises the main warps only.
 // kPlain: the evaluation stores no residual vector and takes no adjoint seeds (loss and g = J^T r only -- the solver
 // steps): compiled without the residual-row addressing of the general form
-template <int NW, int U1, int UL, bool kPlain>
+// kFull: full checkpoints (the default mode) known at compile time -- the recompute paths of the other modes drop out
+template <int NW, int U1, int UL, bool kPlain, bool kFull>
 __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
     trx_rollout_kernel(const __grid_constant__ KHeader hdr, const __grid_constant__ KArgs a) {
   double *const a_r_out = kPlain ? nullptr : a.r_out;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
   // kinematics and contacts only
   const int T = a.frames, CK = H[H_CKPT];
   const int CKX = a.ckpt_doubles;  // stride
-  const int mode = a.ckpt_mode;
+  const int mode = kFull ? 2 : a.ckpt_mode;
   // offsets of the optional parts inside a checkpoint
   // (every segment starts on a 16-byte boundary and is an even number of doubles: bulk copies move them whole)
   const int ev = 1;  // round up to even
@@ -788,9 +789,11 @@ namespace {
 typedef void (*KernelFn)(const KHeader, const KArgs);
 struct Variant {
   int nw, u1, ul;  // rollouts per CTA, dW tiles per warp of the first / last layer
-  KernelFn fn, fn_plain;  // general form; loss and g = J^T r only
+  KernelFn fn[2][2];  // [loss and g = J^T r only][full checkpoints]
 };
-#define RL_VARIANT(NW, U1, UL) {NW, U1, UL, trx_rollout_kernel<NW, U1, UL, false>, trx_rollout_kernel<NW, U1, UL, true>}
+#define RL_VARIANT(NW, U1, UL)                                                                              \
+  {NW, U1, UL, {{trx_rollout_kernel<NW, U1, UL, false, false>, trx_rollout_kernel<NW, U1, UL, false, true>}, \
+                {trx_rollout_kernel<NW, U1, UL, true, false>, trx_rollout_kernel<NW, U1, UL, true, true>}}}
 // smallest first: (2, 7) one-layer and narrow policies, (7, 13) the 41 -> 64 -> 83 policy of the benchmark (20 tiles
 // = 80 of the 128 registers a thread of a 16-warp CTA can have), 4 rollouts per CTA when 8 regions do not fit the
 // shared memory.  Wider policies have no re-rolled form here (TRX_ERR_UNSUPPORTED: use the tape objective).
@@ -909,8 +912,8 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   ro->nw = pick->nw;
   ro->u1 = pick->u1;
   ro->ul = pick->ul;
-  RL_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
-  RL_CUDA(cudaFuncSetAttribute(pick->fn_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
+  for (int i = 0; i < 4; i++)
+    RL_CUDA(cudaFuncSetAttribute(pick->fn[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ro->smem_bytes));
 
   // ---- device buffers; rollouts are walked in chunks when the checkpoints exceed the byte budget
   // what a checkpoint holds beyond the carried state: the more, the less the adjoint sweep
@@ -1010,7 +1013,7 @@ trx_status trxRolloutEvaluate(trx_rollout *ro, const double *d_x, double *d_out,
   RL_CUDA(cudaSetDevice(ro->device));
   KernelFn fn = nullptr;
   for (const Variant &v : kVariants)
-    if (v.nw == ro->nw && v.u1 == ro->u1 && v.ul == ro->ul) fn = (d_r || d_seed) ? v.fn : v.fn_plain;
+    if (v.nw == ro->nw && v.u1 == ro->u1 && v.ul == ro->ul) fn = v.fn[(d_r || d_seed) ? 0 : 1][ro->args.ckpt_mode == 2 ? 1 : 0];
   KArgs a = ro->args;
   a.x = d_x;
   a.r_out = d_r;
