@@ -333,7 +333,10 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
           phaseBody(cb);
         }
         barAll();  // B
-        if (step < T) continue;
+        if (step < T) {
+          if (mode == 2) barAll();  // S
+          continue;
+        }
         const int f_next = 2 * T - 2 - step;  // the frame of the next step
         barAll();  // C
         if (mode == 2) fetchCheckpoint(grp, f_next, 1, nt);
@@ -371,7 +374,30 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
         }
         barAll();  // A
         barAll();  // B
-        if (step < T) continue;
+        if (step < T) {
+          if (mode == 2) {
+            barAll();  // S: the frame's values are final; the main warps go on with the last contact phase
+            // the frame's checkpoint beyond the carried state: thread = (rollout, slot) over the dW warps
+            const int rr = htid & (NW - 1), sl = htid / NW;
+            constexpr int ns = NTD / NW;
+            const long local = (long)grp * NW + rr;
+            if (local < a.count) {
+              double *ck = a.ckpt + ((size_t)local * T + step) * CKX;
+              const double *reg = sm + a.o_region + rr * H[H_REGION];
+              const double *hr = HS + rr * a.s_H, *ar = AS + rr * a.s_H, *outr = OS + rr * a.s_O, *xr = XS + rr * a.s_X;
+              const int n_pose = H[H_NJ] * 7, nqv = H[H_NQ];
+              double *cp = ck + CK_POLICY;
+              for (int e = sl; e < seg_h; e += ns) cp[e] = e < n_hid ? hr[e] : 0.0, cp[seg_h + e] = e < n_hid ? ar[e] : 0.0;
+              for (int e = sl; e < seg_o; e += ns) cp[2 * seg_h + e] = e < n_out ? outr[e] : 0.0;
+              for (int e = sl; e < seg_v; e += ns) cp[2 * seg_h + seg_o + e] = e < nqv ? reg[H[R_VEL] + e] : 0.0;
+              for (int e = sl; e < seg_pose; e += ns) ck[CK_FULL + e] = e < n_pose ? reg[H[R_POSE] + e] : 0.0;
+              for (int e = sl; e < seg_x; e += ns) ck[CK_X + e] = e < n_in ? xr[e] : 0.0;
+              for (int e = sl; e < seg_ee; e += ns) ck[CK_EE + e] = reg[H[R_EE] + (e / 12) * EE_STRIDE + e % 12];
+              for (int e = sl; e < 4; e += ns) ck[CK_CG + e] = e < 3 ? reg[H[R_CG] + e] : 0.0;
+            }
+          }
+          continue;
+        }
         const int f_next = 2 * T - 2 - step;  // the frame of the next step
         barAll();  // C: output adjoint of the last layer complete
         if (mode == 2) fetchCheckpoint(grp, f_next, 1, nt);
@@ -634,7 +660,7 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
                                }
                              }));
             PH(3, barMain<NTM>());
-            if (!rec && mode >= 1 && active) {
+            if (!rec && mode == 1 && active) {
               double *cp = ckpt + (size_t)f * CKX + CK_POLICY;
               for (int e = slot; e < seg_h; e += 32) cp[e] = e < n_hid ? c.h[e] : 0.0, cp[seg_h + e] = e < n_hid ? c.a[e] : 0.0;
               for (int e = slot; e < seg_o; e += 32) cp[2 * seg_h + e] = e < n_out ? c.out[e] : 0.0;
@@ -642,16 +668,10 @@ __global__ void __launch_bounds__((NW + kHelperWarps) * 32, 1)
             }
           }
           PH(8, if (active) { if (rec) phaseContact1<false>(c, slot, f, loss); else phaseContact1<true>(c, slot, f, loss); } barMain<NTM>());
-          PH(9, if (active) phaseContact2(c, slot, f); barMain<NTM>());
+          // S (full checkpoints, forward sweep): everything a checkpoint holds beyond the carried state is final -- the dW
+          // warps, idle in this sweep, copy it out while the main warps finish the frame
+          PH(9, if (active) phaseContact2(c, slot, f); if (!rec && mode == 2) barAll(); else barMain<NTM>());
           if (!rec) {
-            if (mode == 2 && active) {
-              double *ck = ckpt + (size_t)f * CKX;
-              const int n_pose = H[H_NJ] * 7;
-              for (int e = slot; e < seg_pose; e += 32) ck[CK_FULL + e] = e < n_pose ? c.s[H[R_POSE] + e] : 0.0;
-              for (int e = slot; e < seg_x; e += 32) ck[CK_X + e] = e < n_in ? c.x[e] : 0.0;
-              for (int e = slot; e < seg_ee; e += 32) ck[CK_EE + e] = c.s[H[R_EE] + (e / 12) * EE_STRIDE + e % 12];
-              for (int e = slot; e < 4; e += 32) ck[CK_CG + e] = e < 3 ? c.s[H[R_CG] + e] : 0.0;
-            }
             PH(10, if (active) phaseContact3(c, slot, f, loss); barMain<NTM>());
           }
         }
@@ -920,6 +940,7 @@ trx_status trxRolloutCreate(const char *options, uint64_t lanes, uint64_t max_de
   // recomputes and the more crosses HBM.  TRX_ROLLOUT_CHECKPOINT = 0 | 1 | 2 overrides the default.
   a.ckpt_mode = checkpoint_mode;
   if (const char *w = getenv("TRX_ROLLOUT_CHECKPOINT")) a.ckpt_mode = std::max(0, std::min(2, atoi(w)));
+  if (n_layers == 0) a.ckpt_mode = std::min(a.ckpt_mode, 1);  // the full restore / store is synchronised inside the policy's phases
   auto even = [](int n) { return (n + 1) & ~1; };
   a.ckpt_doubles = even(I[H_CKPT]);
   if (a.ckpt_mode >= 1) a.ckpt_doubles += 2 * even(n_hid) + even(n_out) + even(I[H_NQ]);
