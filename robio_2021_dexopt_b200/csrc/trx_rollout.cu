@@ -169,14 +169,16 @@ __device__ __forceinline__ void cpAsync16(double *dst_shared, const double *src_
 constexpr int kHelperWarps = 8;            // helper warps of a CTA:
 constexpr int kDwWarps = kHelperWarps - 1;  // weight-gradient warps, and one body warp
 
-// One CTA = one group of NW rollouts at a time, NW main warps + 4 helper warps:
+// One CTA = one group of NW rollouts at a time, NW main warps + 8 helper warps:
 //   main warps     the frame phases (rollout_frame.h), the policy layers and their input adjoints (DMMA tiles)
 //   helper warps   what is off the frame's critical path: the body step and its adjoint (helper warp 0, a lane per
 //                  rollout) while the main warps run the forward kinematics, and the weight gradients dW = X^T GY
 //                  (register accumulators: U1 tiles of the first layer of a two-layer policy and UL tiles of the
 //                  last layer per helper warp, over all frames and groups of the CTA) plus the bias gradients
-//                  while the main warps go on with the adjoint of the frame.
-// The two sides meet at the full barriers A..G of a step; everything else synchronises the main warps only.
+//                  while the main warps go on with the adjoint of the frame.  In the forward sweep, where there is
+//                  no dW, the same warps write the frame's checkpoint beyond the carried state (full checkpoints).
+// The two sides meet at the full barriers of a step (forward: A, B, S; adjoint: A..G); everything else synchronises
+// the main warps only.
 // kPlain: the evaluation stores no residual vector and takes no adjoint seeds (loss and g = J^T r only -- the solver
 // steps): compiled without the residual-row addressing of the general form
 // kFull: full checkpoints (the default mode) known at compile time -- the recompute paths of the other modes drop out
